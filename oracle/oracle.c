@@ -1,0 +1,553 @@
+/*
+ * oracle.c -- CPU restatement of the wgpu-mm hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file is the checker, never the product: only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.  The product
+ * (wgpu_mm_b200/, include/b200mm.h) never links or calls anything here and fails
+ * loudly when its CUDA library is missing.
+ *
+ * Pinning status:
+ *   - sint8_quantize / sint8_dequantize: PINNED by the reference's only golden
+ *     vector, src/quant.rs:48-64 (test_qdq), reproduced in tests/test_oracle.py.
+ *   - mm_ref and every WGSL restatement: the reference holds no stored outputs and
+ *     uses an unseeded RNG (src/harness.rs:111), and its own toolchain (nightly Rust +
+ *     wgpu git master + a Vulkan ICD) is absent from this image, so bit-level parity
+ *     with the WGSL output is "parity unpinned".  What IS pinned is the reference's
+ *     tolerance gate: max-abs-error <= 1e-3 against mm_ref (src/harness.rs:82).  The
+ *     restatements are cross-checked against each other and an FP64 GEMM.
+ *
+ * All paths cited are relative to /root/reference.
+ * Build: see oracle/Makefile (gcc -O2 -fopenmp -ffp-contract=off: no silent FMA contraction,
+ * because Rust never contracts a*b+c; kernels that call WGSL fma() use fmaf explicitly).
+ */
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORACLE_API __attribute__((visibility("default")))
+
+ORACLE_API int oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+ORACLE_API void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Synthetic data.  The reference draws Uniform[-10,10) / 50 from an UNSEEDED thread_rng
+ * (src/harness.rs:103-121), so only the distribution can be reproduced.  We add a seed and
+ * use a counter-based generator (splitmix64 of seed+index) so that the CUDA side
+ * (csrc/kernels/datagen.cuh) can regenerate bit-identical values on the device.
+ * ------------------------------------------------------------------------------------------ */
+static inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+static inline float weight_value(uint64_t seed, uint64_t i) {
+    uint32_t u24 = (uint32_t)(splitmix64(seed * 0xD1342543DE82EF95ull + i) >> 40); /* 24 random bits */
+    float f = (float)u24 * (1.0f / 16777216.0f);                                  /* [0,1) exact   */
+    float x = f * 20.0f - 10.0f;                                                  /* [-10,10)      */
+    return x / 50.0f;                                                             /* harness.rs:116 */
+}
+
+/* src/harness.rs:103-121 generate_weight_data (seeded restatement). */
+ORACLE_API void oracle_generate_weight_data(uint64_t seed, float* out, size_t n) {
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; ++i) out[i] = weight_value(seed, (uint64_t)i);
+}
+
+/* Same stream, but starting at element `offset` (used for N-sharded panels). */
+ORACLE_API void oracle_generate_weight_data_at(uint64_t seed, uint64_t offset, float* out, size_t n) {
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; ++i) out[i] = weight_value(seed, offset + (uint64_t)i);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * mm_ref -- src/harness.rs:17-28.  fp32, k-sequential, multiply then add (Rust never fuses).
+ * oracle_mm_ref_literal is the triple loop exactly as written.  oracle_mm_ref reorders the
+ * loops to (m,k,n) with a row of accumulators: every C[m,n] still receives its products in
+ * k = 0..K-1 order with the same roundings, so the result is bit-identical (asserted in
+ * tests/test_oracle.py) but it vectorises across n and parallelises across m.
+ * ------------------------------------------------------------------------------------------ */
+ORACLE_API void oracle_mm_ref_literal(const float* A, const float* B, float* C, size_t M, size_t N, size_t K) {
+    for (size_t m = 0; m < M; ++m) {
+        for (size_t n = 0; n < N; ++n) {
+            float res = 0.f;
+            for (size_t k = 0; k < K; ++k) {
+                float p = A[m * K + k] * B[k * N + n];
+                res = res + p;
+            }
+            C[m * N + n] = res;
+        }
+    }
+}
+
+ORACLE_API void oracle_mm_ref(const float* A, const float* B, float* C, size_t M, size_t N, size_t K) {
+    /* For M == 1 (GEMV) parallelise over column blocks instead of rows. */
+    const size_t NB = 1024;
+    const size_t nblk = (N + NB - 1) / NB;
+#pragma omp parallel for collapse(2) schedule(dynamic, 1)
+    for (size_t m = 0; m < M; ++m) {
+        for (size_t b = 0; b < nblk; ++b) {
+            size_t n0 = b * NB, n1 = n0 + NB < N ? n0 + NB : N;
+            float acc[1024];
+            for (size_t n = n0; n < n1; ++n) acc[n - n0] = 0.f;
+            for (size_t k = 0; k < K; ++k) {
+                const float a = A[m * K + k];
+                const float* brow = B + k * N;
+                for (size_t n = n0; n < n1; ++n) {
+                    float p = a * brow[n];
+                    acc[n - n0] = acc[n - n0] + p;
+                }
+            }
+            for (size_t n = n0; n < n1; ++n) C[m * N + n] = acc[n - n0];
+        }
+    }
+}
+
+/* north_star's accuracy oracle: FP64 host GEMM of the fp32 inputs.  Output is double. */
+ORACLE_API void oracle_mm_f64(const float* A, const float* B, double* C, size_t M, size_t N, size_t K) {
+    const size_t NB = 512;
+    const size_t nblk = (N + NB - 1) / NB;
+#pragma omp parallel for collapse(2) schedule(dynamic, 1)
+    for (size_t m = 0; m < M; ++m) {
+        for (size_t b = 0; b < nblk; ++b) {
+            size_t n0 = b * NB, n1 = n0 + NB < N ? n0 + NB : N;
+            double acc[512];
+            for (size_t n = n0; n < n1; ++n) acc[n - n0] = 0.0;
+            for (size_t k = 0; k < K; ++k) {
+                const double a = (double)A[m * K + k];
+                const float* brow = B + k * N;
+                for (size_t n = n0; n < n1; ++n) acc[n - n0] += a * (double)brow[n];
+            }
+            for (size_t n = n0; n < n1; ++n) C[m * N + n] = acc[n - n0];
+        }
+    }
+}
+
+/* FP64 GEMM restricted to a list of rows of C (sampled verification at 16384^3).
+ * C_rows is nrows x N, row i holding C[rows[i], :]. */
+ORACLE_API void oracle_mm_f64_rows(const float* A, const float* B, double* C_rows, const int64_t* rows,
+                                   size_t nrows, size_t N, size_t K) {
+    const size_t NB = 512;
+    const size_t nblk = (N + NB - 1) / NB;
+#pragma omp parallel for collapse(2) schedule(dynamic, 1)
+    for (size_t r = 0; r < nrows; ++r) {
+        for (size_t b = 0; b < nblk; ++b) {
+            size_t m = (size_t)rows[r];
+            size_t n0 = b * NB, n1 = n0 + NB < N ? n0 + NB : N;
+            double acc[512];
+            for (size_t n = n0; n < n1; ++n) acc[n - n0] = 0.0;
+            for (size_t k = 0; k < K; ++k) {
+                const double a = (double)A[m * K + k];
+                const float* brow = B + k * N;
+                for (size_t n = n0; n < n1; ++n) acc[n - n0] += a * (double)brow[n];
+            }
+            for (size_t n = n0; n < n1; ++n) C_rows[r * N + n] = acc[n - n0];
+        }
+    }
+}
+
+/* src/harness.rs:64-70: "mae" is a MAX absolute error. */
+ORACLE_API float oracle_max_abs_err(const float* gpu, const float* cpu, size_t n) {
+    float mae = 0.0f;
+    for (size_t i = 0; i < n; ++i) {
+        float diff = fabsf(gpu[i] - cpu[i]);
+        if (diff > mae) mae = diff;
+        if (diff != diff) return NAN; /* NaN must not pass the gate silently */
+    }
+    return mae;
+}
+
+/* max |gpu - ref64| and max |ref64| (for the north_star relative-error report). */
+ORACLE_API void oracle_err_vs_f64(const float* gpu, const double* ref, size_t n, double* max_abs_err,
+                                  double* max_abs_ref) {
+    double e = 0.0, r = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+        double d = fabs((double)gpu[i] - ref[i]);
+        if (d != d) { e = NAN; break; }
+        if (d > e) e = d;
+        double a = fabs(ref[i]);
+        if (a > r) r = a;
+    }
+    *max_abs_err = e;
+    *max_abs_ref = r;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Quant codec -- src/quant.rs:7-43.
+ * Rust semantics restated: f32::round = half away from zero (roundf); `as i32` on a float is a
+ * saturating cast (NaN -> 0); packing is little-endian, element 0 in the low byte.
+ * ------------------------------------------------------------------------------------------ */
+static inline int32_t rust_f32_as_i32(float v) {
+    if (v != v) return 0;
+    if (v >= 2147483648.0f) return INT32_MAX;
+    if (v <= -2147483648.0f) return INT32_MIN;
+    return (int32_t)v;
+}
+
+/* src/quant.rs:7-28.  Returns absmax. */
+ORACLE_API float oracle_sint8_quantize(const float* matrix, size_t K, size_t N, uint32_t* out) {
+    const size_t len = K * N;
+    float absmax = 0.f;
+    for (size_t i = 0; i < len; ++i) {
+        float a = fabsf(matrix[i]);
+        if (a > absmax) absmax = a; /* fold(zero, max(abs)) quant.rs:17; f32::max ignores NaN */
+    }
+    const float sf = 127.f;
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < len; i += 4) {
+        uint32_t w = 0;
+        for (int j = 0; j < 4; ++j) {
+            float q = roundf(matrix[i + j] / absmax * sf); /* quant.rs:21-24 */
+            w |= ((uint32_t)rust_f32_as_i32(q) & 0xFFu) << (8 * j);
+        }
+        out[i / 4] = w;
+    }
+    return absmax;
+}
+
+/* src/quant.rs:30-43.  (w << s) >> 24 on i32 sign-extends one byte; then / 127.0 * absmax. */
+ORACLE_API void oracle_sint8_dequantize(const uint32_t* q, float absmax, size_t K, size_t N, float* out) {
+    const size_t len = K * N;
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < len; i += 4) {
+        int32_t p = (int32_t)q[i / 4];
+        out[i + 0] = (float)((int32_t)((uint32_t)p << 24) >> 24) / 127.0f * absmax;
+        out[i + 1] = (float)((int32_t)((uint32_t)p << 16) >> 24) / 127.0f * absmax;
+        out[i + 2] = (float)((int32_t)((uint32_t)p << 8) >> 24) / 127.0f * absmax;
+        out[i + 3] = (float)(p >> 24) / 127.0f * absmax;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * WGSL restatements.  One simulated invocation per loop iteration, dispatch geometry taken
+ * from src/gemm.rs / src/gemv.rs (or inferred for the orphan shaders), so an
+ * index-algebra mistake shows up as a wrong result rather than being papered over.
+ * WGSL lets the back-end contract a*b+c and reorder nothing else; we restate `+=` of a product
+ * as unfused mul,add and fma() as fmaf.
+ * ------------------------------------------------------------------------------------------ */
+
+/* shaders/gemm/gemm_1.wgsl:12-28; geometry src/gemm.rs:16-32: wg (16,16,1), count (ceil(M/16),ceil(N/16),1). */
+ORACLE_API void oracle_wgsl_gemm_1(const float* A, const float* B, float* C, size_t M, size_t N, size_t K) {
+    size_t gx = (M + 15) / 16 * 16, gy = (N + 15) / 16 * 16;
+#pragma omp parallel for schedule(static)
+    for (size_t x = 0; x < gx; ++x)
+        for (size_t y = 0; y < gy; ++y) {
+            if (x < M && y < N) {
+                float tmp = 0.f;
+                for (size_t i = 0; i < K; ++i) {
+                    float p = A[x * K + i] * B[i * N + y];
+                    tmp = tmp + p;
+                }
+                C[x * N + y] = tmp;
+            }
+        }
+}
+
+/* shaders/gemm/gemm_1v.wgsl:12-32; src/gemm.rs:34-50: wg (16,4,1), count (ceil(M/16),ceil(N/16),1). */
+ORACLE_API void oracle_wgsl_gemm_1v(const float* A, const float* B, float* C, size_t M, size_t N, size_t K) {
+    size_t gx = (M + 15) / 16 * 16, gy = (N + 15) / 16 * 4;
+#pragma omp parallel for schedule(static)
+    for (size_t cRow = 0; cRow < gx; ++cRow)
+        for (size_t cCol = 0; cCol < gy; ++cCol) {
+            if (cRow < M && cCol < N / 4) {
+                float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+                for (size_t k = 0; k < K / 4; ++k) {
+                    const float* a = A + (cRow * K / 4 + k) * 4;
+                    for (int c = 0; c < 4; ++c) {
+                        const float* b = B + (k * N + cCol + (size_t)c * N / 4) * 4; /* vec4 index */
+                        for (int j = 0; j < 4; ++j) {
+                            float p = a[c] * b[j];
+                            tmp[j] = tmp[j] + p;
+                        }
+                    }
+                }
+                for (int j = 0; j < 4; ++j) C[(cRow * N / 4 + cCol) * 4 + j] = tmp[j];
+            }
+        }
+}
+
+/* shaders/gemm/gemm_2.wgsl:12-30; src/gemm.rs:52-67: wg (256,1,1), count (ceil(M/16),ceil(N/16),1). */
+ORACLE_API void oracle_wgsl_gemm_2(const float* A, const float* B, float* C, size_t M, size_t N, size_t K) {
+    size_t wx = (M + 15) / 16, wy = (N + 15) / 16;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (size_t gx = 0; gx < wx; ++gx)
+        for (size_t gy = 0; gy < wy; ++gy)
+            for (size_t lid = 0; lid < 256; ++lid) {
+                size_t cRow = gx * 16 + lid / 16, cCol = gy * 16 + lid % 16;
+                if (cRow < M && cCol < N) {
+                    float tmp = 0.f;
+                    for (size_t i = 0; i < K; ++i) {
+                        float p = A[cRow * K + i] * B[i * N + cCol];
+                        tmp = tmp + p;
+                    }
+                    C[cRow * N + cCol] = tmp;
+                }
+            }
+}
+
+/* shaders/gemm/gemm_3.wgsl:12-49 (BLOCKSIZE 16, explicit fma); src/gemm.rs:69-90.
+ * Per output the accumulation is k-sequential fma, so the smem staging is not simulated. */
+ORACLE_API void oracle_wgsl_gemm_3(const float* A, const float* B, float* C, size_t M, size_t N, size_t K) {
+#pragma omp parallel for schedule(static)
+    for (size_t m = 0; m < M; ++m)
+        for (size_t n = 0; n < N; ++n) {
+            float tmp = 0.f;
+            for (size_t k = 0; k < K; ++k) tmp = fmaf(A[m * K + k], B[k * N + n], tmp);
+            C[m * N + n] = tmp;
+        }
+}
+
+/* shaders/gemm/gemm_4.wgsl:15-63 (BM=BN=16,BK=8,TM=2) and gemm_5.wgsl:15-86 (BM=BN=32,BK=16,TM=TN=4);
+ * src/gemm.rs:92-150.  Simulated per workgroup / per thread including the cooperative smem loads. */
+ORACLE_API void oracle_wgsl_gemm_4(const float* A, const float* B, float* C, size_t M, size_t N, size_t K) {
+    enum { BM = 16, BN = 16, BK = 8, TM = 2, NT = BM * BN / TM };
+    size_t wx = (N + BN - 1) / BN, wy = (M + BM - 1) / BM; /* x<->N, y<->M: src/gemm.rs:109 */
+#pragma omp parallel for collapse(2) schedule(static)
+    for (size_t cRow = 0; cRow < wy; ++cRow)
+        for (size_t cCol = 0; cCol < wx; ++cCol) {
+            float As[BM * BK], Bs[BK * BN], res[NT][TM];
+            memset(res, 0, sizeof(res));
+            size_t aIdx = cRow * BM * K, bIdx = cCol * BN, cIdx = cRow * BM * N + cCol * BN;
+            for (size_t bk = 0; bk < K; bk += BK) {
+                for (size_t t = 0; t < NT; ++t) {
+                    size_t icA = t % BK, irA = t / BK, icB = t % BN, irB = t / BN;
+                    As[irA * BK + icA] = A[aIdx + irA * K + icA];
+                    Bs[irB * BN + icB] = B[bIdx + irB * N + icB];
+                }
+                aIdx += BK;
+                bIdx += BK * N;
+                for (size_t t = 0; t < NT; ++t) {
+                    size_t tc = t % BN, tr = t / BN;
+                    for (size_t d = 0; d < BK; ++d) {
+                        float tmpB = Bs[d * BN + tc];
+                        for (size_t r = 0; r < TM; ++r) res[t][r] = fmaf(As[(tr * TM + r) * BK + d], tmpB, res[t][r]);
+                    }
+                }
+            }
+            for (size_t t = 0; t < NT; ++t) {
+                size_t tc = t % BN, tr = t / BN;
+                for (size_t r = 0; r < TM; ++r) C[cIdx + (tr * TM + r) * N + tc] = res[t][r];
+            }
+        }
+}
+
+ORACLE_API void oracle_wgsl_gemm_5(const float* A, const float* B, float* C, size_t M, size_t N, size_t K) {
+    enum { BM = 32, BN = 32, BK = 16, TM = 4, TN = 4, NT = BM * BN / (TM * TN) };
+    size_t wx = (N + BN - 1) / BN, wy = (M + BM - 1) / BM;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (size_t cRow = 0; cRow < wy; ++cRow)
+        for (size_t cCol = 0; cCol < wx; ++cCol) {
+            float As[BM * BK], Bs[BK * BN], res[NT][TM * TN];
+            memset(res, 0, sizeof(res));
+            size_t aIdx = cRow * BM * K, bIdx = cCol * BN, cIdx = cRow * BM * N + cCol * BN;
+            const size_t strideA = NT / BK, strideB = NT / BN;
+            for (size_t bk = 0; bk < K; bk += BK) {
+                for (size_t t = 0; t < NT; ++t) {
+                    size_t icA = t % BK, irA = t / BK, icB = t % BN, irB = t / BN;
+                    for (size_t lo = 0; lo < BM; lo += strideA) As[(irA + lo) * BK + icA] = A[aIdx + (irA + lo) * K + icA];
+                    for (size_t lo = 0; lo < BK; lo += strideB) Bs[(irB + lo) * BN + icB] = B[bIdx + (irB + lo) * N + icB];
+                }
+                aIdx += BK;
+                bIdx += BK * N;
+                for (size_t t = 0; t < NT; ++t) {
+                    size_t tc = t % (BN / TN), tr = t / (BN / TN);
+                    float regM[TM], regN[TN];
+                    for (size_t d = 0; d < BK; ++d) {
+                        for (size_t i = 0; i < TM; ++i) regM[i] = As[(tr * TM + i) * BK + d];
+                        for (size_t i = 0; i < TN; ++i) regN[i] = Bs[d * BN + tc * TN + i];
+                        for (size_t rm = 0; rm < TM; ++rm)
+                            for (size_t rn = 0; rn < TN; ++rn)
+                                res[t][rm * TN + rn] = fmaf(regM[rm], regN[rn], res[t][rm * TN + rn]);
+                    }
+                }
+            }
+            for (size_t t = 0; t < NT; ++t) {
+                size_t tc = t % (BN / TN), tr = t / (BN / TN);
+                for (size_t rm = 0; rm < TM; ++rm)
+                    for (size_t rn = 0; rn < TN; ++rn)
+                        C[cIdx + (tr * TM + rm) * N + tc * TN + rn] = res[t][rm * TN + rn];
+            }
+        }
+}
+
+/* shaders/gemm.wgsl:11-14 + shaders/gemm_macro.wgsl:2-53 (WONNX mat4x4 kernel; BASELINE config 0).
+ * 1-D grid of M*N/16 invocations.  product = mat_right * mat_left, columns of a WGSL mat4x4 are
+ * vec4s: product[j] = sum_i mat_right[i] * mat_left[j][i]  (i-sequential), then result[j] += product[j]
+ * -- i.e. blocked-by-4 summation.  The spurious workgroupBarrier() (:24) has no arithmetic effect. */
+ORACLE_API void oracle_wgsl_gemm_wonnx(const float* A, const float* B, float* C, size_t M, size_t N, size_t K) {
+    const size_t n4 = N / 4, inv = M * N / 16;
+#pragma omp parallel for schedule(static)
+    for (size_t g = 0; g < inv; ++g) {
+        size_t y = g % n4, x = g / n4;
+        float result[4][4];
+        memset(result, 0, sizeof(result));
+        for (size_t k = 0; k < K / 4; ++k) {
+            const float *left[4], *right[4];
+            for (int i = 0; i < 4; ++i) {
+                left[i] = A + ((x * K + k) + (size_t)i * K / 4) * 4;  /* row 4x+i, cols 4k..4k+3 */
+                right[i] = B + ((k * N + y) + (size_t)i * N / 4) * 4; /* row 4k+i, cols 4y..4y+3 */
+            }
+            for (int j = 0; j < 4; ++j) {
+                float prod[4];
+                for (int c = 0; c < 4; ++c) prod[c] = right[0][c] * left[j][0];
+                for (int i = 1; i < 4; ++i)
+                    for (int c = 0; c < 4; ++c) {
+                        float p = right[i][c] * left[j][i];
+                        prod[c] = prod[c] + p;
+                    }
+                for (int c = 0; c < 4; ++c) result[j][c] = result[j][c] + prod[c];
+            }
+        }
+        for (int j = 0; j < 4; ++j)
+            for (int c = 0; c < 4; ++c) C[((x * N + y) + (size_t)j * N / 4) * 4 + c] = result[j][c];
+    }
+}
+
+/* shaders/bram.wgsl:11-50 and shaders/bram8x8.wgsl:10-50 (identical bodies).  The shader hard-codes
+ * 256u = 1024/4; restated with K/4 and N/4 so other sizes can be exercised (at 1024^3 they coincide).
+ * gid.x in [0,M/4) -> rows 4m..4m+3, gid.y in [0,N/4) -> vec4 column n. Per output k-sequential mul,add. */
+ORACLE_API void oracle_wgsl_bram(const float* A, const float* B, float* C, size_t M, size_t N, size_t K) {
+    const size_t k4 = K / 4, n4 = N / 4;
+#pragma omp parallel for schedule(static)
+    for (size_t m = 0; m < M / 4; ++m)
+        for (size_t n = 0; n < n4; ++n) {
+            float r[4][4];
+            memset(r, 0, sizeof(r));
+            for (size_t k = 0; k < k4; ++k) {
+                for (int c = 0; c < 4; ++c) { /* c = x,y,z,w component of a_i; b row 4k+c */
+                    const float* b = B + ((k * 4 + c) * n4 + n) * 4;
+                    for (int i = 0; i < 4; ++i) {
+                        float a = A[((m * 4 + i) * k4 + k) * 4 + c];
+                        for (int j = 0; j < 4; ++j) {
+                            float p = a * b[j];
+                            r[i][j] = r[i][j] + p;
+                        }
+                    }
+                }
+            }
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) C[((m * 4 + i) * n4 + n) * 4 + j] = r[i][j];
+        }
+}
+
+/* shaders/gemm3.wgsl:11-92 (webgpu-blas 4x8 register tile; hard-coded KD4=ND4=256u restated as K/4,N/4).
+ * x = gid.x in [0,N/8), y = gid.y in [0,M/4).  result = vec4(a.c)*brow + result, k-sequential. */
+ORACLE_API void oracle_wgsl_gemm3(const float* A, const float* B, float* C, size_t M, size_t N, size_t K) {
+    const size_t k4 = K / 4, n4 = N / 4;
+#pragma omp parallel for schedule(static)
+    for (size_t y = 0; y < M / 4; ++y)
+        for (size_t x = 0; x < N / 8; ++x) {
+            float r[4][8];
+            memset(r, 0, sizeof(r));
+            for (size_t k = 0; k < k4; ++k)
+                for (int c = 0; c < 4; ++c) {
+                    const float* b = B + ((k * 4 + c) * n4 + x * 2) * 4; /* 8 consecutive columns */
+                    for (int i = 0; i < 4; ++i) {
+                        float a = A[((y * 4 + i) * k4 + k) * 4 + c];
+                        for (int j = 0; j < 8; ++j) {
+                            float p = a * b[j];
+                            r[i][j] = p + r[i][j];
+                        }
+                    }
+                }
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 8; ++j) C[((y * 4 + i) * n4 + x * 2) * 4 + j] = r[i][j];
+        }
+}
+
+/* WGSL unpack4x8snorm component: max(int8 / 127, -1). */
+static inline float snorm8(uint32_t w, int i) {
+    int32_t q = (int32_t)(int8_t)((w >> (8 * i)) & 0xFFu);
+    float v = (float)q / 127.0f;
+    return v < -1.0f ? -1.0f : v;
+}
+
+/* shaders/gemv/qgemv_1.wgsl:10-39; geometry src/gemv.rs:17-33: wg (8,1), count (ceil(N/32), batch, 1).
+ * Invocation gid.x owns outputs 4g..4g+3; per k-block of 4: right_i = unpack(B[..]) * absmax (rows 4k+i),
+ * result[c] += dot(left, (right_0[c],right_1[c],right_2[c],right_3[c])).  dot is restated as
+ * ((l.x*r0 + l.y*r1) + l.z*r2) + l.w*r3 (order is implementation-defined in WGSL).
+ * `batch` exercises the gid.y offsets (:12-14) that the reference harness never dispatches. */
+ORACLE_API void oracle_wgsl_qgemv_1(const float* A, const uint32_t* Bq, float* C, size_t batch, size_t N, size_t K,
+                                    float absmax) {
+    const size_t n4 = N / 4, k4 = K / 4;
+    const size_t gx = (N + 31) / 32 * 8;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (size_t gy = 0; gy < batch; ++gy)
+        for (size_t g = 0; g < gx; ++g) {
+            if (g >= n4) continue; /* out-of-range lanes of the last workgroup (unchecked in WGSL; N%32==0 in the reference) */
+            const float* left_base = A + gy * k4 * 4;
+            const uint32_t* right_base = Bq + gy * (K * N / 4);
+            float result[4] = {0.f, 0.f, 0.f, 0.f};
+            for (size_t k = 0; k < k4; ++k) {
+                const float* left = left_base + k * 4;
+                float right[4][4];
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t w = right_base[g + k * N + (size_t)i * n4];
+                    for (int c = 0; c < 4; ++c) right[i][c] = snorm8(w, c) * absmax;
+                }
+                for (int c = 0; c < 4; ++c) {
+                    float d = left[0] * right[0][c];
+                    for (int i = 1; i < 4; ++i) {
+                        float p = left[i] * right[i][c];
+                        d = d + p;
+                    }
+                    result[c] = result[c] + d;
+                }
+            }
+            for (int c = 0; c < 4; ++c) C[(gy * n4 + g) * 4 + c] = result[c];
+        }
+}
+
+/* Reference semantics of the quantised test (src/harness.rs:42-48,58): mm_ref(A, dequant(Bq, ABSMAX)). */
+ORACLE_API void oracle_qgemv_ref(const float* A, const uint32_t* Bq, float* C, size_t M, size_t N, size_t K,
+                                 float absmax) {
+    float* Bd = (float*)malloc(sizeof(float) * K * N);
+    oracle_sint8_dequantize(Bq, absmax, K, N, Bd);
+    oracle_mm_ref(A, Bd, C, M, N, K);
+    free(Bd);
+}
+
+/* FP64 version of the same (accuracy oracle for the quantised path). */
+ORACLE_API void oracle_qgemv_f64(const float* A, const uint32_t* Bq, double* C, size_t M, size_t N, size_t K,
+                                 float absmax) {
+    float* Bd = (float*)malloc(sizeof(float) * K * N);
+    oracle_sint8_dequantize(Bq, absmax, K, N, Bd);
+    oracle_mm_f64(A, Bd, C, M, N, K);
+    free(Bd);
+}
+
+/* src/workload.rs:48-68 compute_dim.  Returns 0 and fills (count,size), or -1 for the
+ * reference's panic!("Compute limits exceeded").  dim: 0=X,1=Y,2=Z. */
+ORACLE_API int oracle_compute_dim(size_t work_items, int dim, uint32_t* count, uint32_t* size) {
+    const size_t max_size = dim == 2 ? 64 : 256, max_count = 65535;
+    if (work_items > max_count) {
+        size_t s = (work_items + max_count - 1) / max_count;
+        size_t c = (work_items + s - 1) / s;
+        if (c > max_count || s > max_size) return -1;
+        *count = (uint32_t)c;
+        *size = (uint32_t)s;
+    } else {
+        *count = (uint32_t)work_items;
+        *size = 1;
+    }
+    return 0;
+}

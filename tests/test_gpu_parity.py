@@ -1,0 +1,286 @@
+"""GPU parity tests: every kernel is called through the C ABI (include/b200mm.h) and compared with the
+CPU oracle on the same seeded inputs.
+
+Tolerances (north_star + reference):
+  GATE      max-abs-error <= 1e-3 vs mm_ref on U[-0.2,0.2) data       src/harness.rs:82 (the reference's gate)
+  REL_F64   max |gpu - fp64| / max |fp64| <= 5e-6                      north_star "max relative error against an FP64 host GEMM"
+  WGSL      faithful ports: BIT-EXACT against their oracle restatement (same per-output arithmetic order)
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GATE = 1e-3
+REL_F64 = 5e-6
+
+
+def _run(ctx, kid, A, B, M, N, K, params=None, grid=None, b_dtype=np.float32):
+    import wgpu_mm_b200 as w
+    kern = ctx.kernel(kid, M, N, K, params)
+    dA = ctx.buffer_from(np.ascontiguousarray(A, dtype=np.float32))
+    dB = ctx.buffer_from(np.ascontiguousarray(B, dtype=b_dtype))
+    batch = params.batch if (params and params.batch) else 1
+    noise = np.full(batch * M * N, 123.25, dtype=np.float32)  # C is overwritten, never accumulated into (src/harness.rs:55)
+    dC = ctx.buffer_from(noise)
+    ctx.launch(kern, dA, dB, dC, grid)
+    out = dC.read(np.float32).reshape(batch * M, N)
+    for b in (dA, dB, dC):
+        b.free()
+    kern.free()
+    return out
+
+
+def _check(oracle, got, A, B, rel=REL_F64):
+    ref = oracle.mm_ref(A, B)
+    assert not np.isnan(got).any()
+    assert oracle.max_abs_err(got, ref) <= GATE
+    e, m = oracle.err_vs_f64(got, oracle.mm_f64(A, B))
+    assert e / m <= rel, f"rel err vs fp64 {e / m:.3e}"
+    return e / m
+
+
+PORTS = ["gemm_1", "gemm_1v", "gemm_2", "gemm_3", "gemm_4", "gemm_5", "gemm_wonnx", "bram", "bram8x8", "gemm3"]
+
+
+@pytest.mark.parametrize("name", PORTS)
+@pytest.mark.parametrize("shape", [(64, 64, 64), (128, 256, 96), (96, 64, 160)])
+def test_wgsl_ports_bit_exact(gpu_ctx, oracle, name, shape):
+    """Faithful ports launched with the entry point's Workload (grid AND block) vs the per-shader restatement."""
+    import wgpu_mm_b200 as w
+    from wgpu_mm_b200.workload import entry_workload
+    M, N, K = shape
+    A = oracle.generate_weight_data(1, M, K)
+    B = oracle.generate_weight_data(2, K, N)
+    wl, kid = entry_workload(name, M, N, K)
+    prm = w.KernelParams(workgroup_size=(wl.size.x, wl.size.y, wl.size.z))
+    got = _run(gpu_ctx, kid, A, B, M, N, K, prm, grid=(wl.count.x, wl.count.y, wl.count.z))
+    want = oracle.wgsl_gemm(name, A, B)
+    assert np.array_equal(got, want), f"{name}: max diff {np.abs(got - want).max():.3e}"
+    _check(oracle, got, A, B)
+
+
+def test_wgsl_ports_at_reference_shape(gpu_ctx, oracle):
+    """1024^3 (src/gemm.rs:5-7), the shape every reference test runs: BASELINE config 0 through gemm.wgsl."""
+    import wgpu_mm_b200 as w
+    from wgpu_mm_b200.workload import entry_workload
+    M = N = K = 1024
+    A = oracle.generate_weight_data(3, M, K)
+    B = oracle.generate_weight_data(4, K, N)
+    for name in ("gemm_wonnx", "gemm_5", "bram"):
+        wl, kid = entry_workload(name, M, N, K)
+        prm = w.KernelParams(workgroup_size=(wl.size.x, wl.size.y, wl.size.z))
+        got = _run(gpu_ctx, kid, A, B, M, N, K, prm, grid=(wl.count.x, wl.count.y, wl.count.z))
+        assert np.array_equal(got, oracle.wgsl_gemm(name, A, B)), name
+        _check(oracle, got, A, B)
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 16), (128, 128, 128), (256, 384, 512), (1024, 1024, 1024)])
+def test_sgemm_simt_aligned(gpu_ctx, oracle, shape):
+    import wgpu_mm_b200 as w
+    M, N, K = shape
+    A = oracle.generate_weight_data(5, M, K)
+    B = oracle.generate_weight_data(6, K, N)
+    got = _run(gpu_ctx, w.KernelId.SGEMM_SIMT, A, B, M, N, K)
+    _check(oracle, got, A, B)
+    # k-sequential fma per output == gemm_5.wgsl's order == oracle_wgsl_gemm_3 (same arithmetic, no tiling simulated)
+    assert np.array_equal(got, oracle.wgsl_gemm("gemm_3", A, B))
+
+
+@pytest.mark.parametrize("shape", [(1, 4, 4), (5, 7, 3), (130, 257, 45), (127, 129, 17), (300, 100, 1000)])
+def test_sgemm_simt_ragged(gpu_ctx, oracle, shape):
+    """Edge tiles: arbitrary M, N, K through the guarded instantiation."""
+    import wgpu_mm_b200 as w
+    M, N, K = shape
+    A = oracle.generate_weight_data(7, M, K)
+    B = oracle.generate_weight_data(8, K, N)
+    got = _run(gpu_ctx, w.KernelId.SGEMM_SIMT, A, B, M, N, K)
+    _check(oracle, got, A, B)
+
+
+@pytest.mark.parametrize("bn", [256, 128])
+@pytest.mark.parametrize("shape", [(128, 256, 32), (128, 256, 256), (256, 512, 1024), (1024, 1024, 1024), (384, 768, 96)])
+def test_sgemm_tc3x(gpu_ctx, oracle, shape, bn):
+    """tcgen05 3xTF32: FP32-accurate (passes the reference gate and the FP64 relative bound)."""
+    import wgpu_mm_b200 as w
+    M, N, K = shape
+    A = oracle.generate_weight_data(9, M, K)
+    B = oracle.generate_weight_data(10, K, N)
+    got = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K, w.KernelParams(tune=(bn, 0, 0, 0)))
+    _check(oracle, got, A, B)
+
+
+@pytest.mark.parametrize("shape", [(100, 36, 20), (129, 260, 36), (500, 1000, 252), (128, 4, 4)])
+def test_sgemm_tc3x_ragged(gpu_ctx, oracle, shape):
+    """TMA zero-fills out-of-range rows / k; the epilogue guards the stores (needs N%4 == K%4 == 0)."""
+    import wgpu_mm_b200 as w
+    M, N, K = shape
+    A = oracle.generate_weight_data(11, M, K)
+    B = oracle.generate_weight_data(12, K, N)
+    got = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K)
+    _check(oracle, got, A, B)
+
+
+def test_sgemm_tc3x_rejects_unaligned(gpu_ctx):
+    import wgpu_mm_b200 as w
+    with pytest.raises(w.B200mmError):
+        gpu_ctx.kernel(w.KernelId.SGEMM_TC3X, 128, 130, 64)
+
+
+def test_sgemm_tc3x_single_pass_fails_the_gate_at_large_k(gpu_ctx, oracle):
+    """1xTF32 cannot hold the reference's 1e-3 gate -- this is why the split exists."""
+    import wgpu_mm_b200 as w
+    M, N, K = 128, 256, 4096
+    A = oracle.generate_weight_data(13, M, K)
+    B = oracle.generate_weight_data(14, K, N)
+    got1 = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K, w.KernelParams(flags=int(w.Flags.TC3X_1X)))
+    got3 = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K)
+    ref = oracle.mm_f64(A, B)
+    e1 = np.abs(got1 - ref).max()
+    e3 = np.abs(got3 - ref).max()
+    assert e3 < 2e-5 and e1 > 20 * e3
+
+
+def test_sgemm_linearity_full_size(gpu_ctx):
+    """4096^3 (BASELINE config 1) through size-independent properties: a rank-1 structured product has a
+    closed form, and C(A, B) restricted to sampled rows equals an FP64 GEMM of those rows."""
+    import wgpu_mm_b200 as w
+    import oracle
+    M = N = K = 4096
+    A = oracle.generate_weight_data(15, M, K)
+    B = oracle.generate_weight_data(16, K, N)
+    rows = np.array([0, 1, 127, 128, 2047, 4095])
+    ref = oracle.mm_f64_rows(A, B, rows)
+    for kid in (w.KernelId.SGEMM_TC3X, w.KernelId.SGEMM_SIMT):
+        got = _run(gpu_ctx, kid, A, B, M, N, K)
+        e, m = oracle.err_vs_f64(got[rows], ref)
+        assert e / m <= REL_F64, (kid, e / m)
+        # checksum of checksums: column sums of C == (column sums of A-rows) applied to B
+        cs = got.astype(np.float64).sum(axis=0)
+        want = A.astype(np.float64).sum(axis=0) @ B.astype(np.float64)
+        assert np.abs(cs - want).max() / np.abs(want).max() < 1e-5
+
+
+GEMV_SHAPES = [(64, 64), (512, 1024), (1000, 260), (4096, 16384), (36, 4)]
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("kn", GEMV_SHAPES)
+def test_gemv_f32(gpu_ctx, oracle, kn, variant):
+    """fp32 GEMV vs mm_ref with M == 1 (the reference has no fp32 GEMV shader)."""
+    import wgpu_mm_b200 as w
+    K, N = kn
+    x = oracle.generate_weight_data(17, 1, K)
+    W = oracle.generate_weight_data(18, K, N)
+    got = _run(gpu_ctx, w.KernelId.GEMV_F32, x, W, 1, N, K, w.KernelParams(tune=(variant, 0, 0, 0)))
+    _check(oracle, got, x, W)
+
+
+@pytest.mark.parametrize("splits", [1, 2, 7, 64])
+def test_gemv_f32_split_k_is_deterministic(gpu_ctx, oracle, splits):
+    import wgpu_mm_b200 as w
+    K, N = 2048, 1024
+    x = oracle.generate_weight_data(19, 1, K)
+    W = oracle.generate_weight_data(20, K, N)
+    prm = w.KernelParams(tune=(0, splits, 0, 0))
+    a = _run(gpu_ctx, w.KernelId.GEMV_F32, x, W, 1, N, K, prm)
+    b = _run(gpu_ctx, w.KernelId.GEMV_F32, x, W, 1, N, K, prm)
+    assert np.array_equal(a, b)
+    _check(oracle, a, x, W)
+
+
+QSHAPES = [(1024, 1024), (64, 64), (4096, 14336), (200, 48), (36, 16)]
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("kn", QSHAPES)
+def test_qgemv_sint8(gpu_ctx, oracle, kn, variant):
+    """Quantised GEMV in the src/quant.rs format with the reference's ABSMAX = 2.0 quirk."""
+    import wgpu_mm_b200 as w
+    K, N = kn
+    x = oracle.generate_weight_data(21, 1, K)
+    W = oracle.generate_weight_data(22, K, N)
+    words, _absmax = oracle.sint8_quantize(W, K, N)  # true absmax discarded, like src/harness.rs:134
+    prm = w.KernelParams(absmax=2.0, batch=1, tune=(variant, 0, 0, 0))
+    got = _run(gpu_ctx, w.KernelId.QGEMV_SINT8, x, words, 1, N, K, prm, b_dtype=np.uint32)
+    ref = oracle.qgemv_ref(x, words, 1, N, K, 2.0)
+    assert oracle.max_abs_err(got, ref) <= GATE
+    e, m = oracle.err_vs_f64(got, oracle.qgemv_f64(x, words, 1, N, K, 2.0))
+    assert e / m <= REL_F64
+    # agreement with the WGSL-order restatement (blocked-by-4 dot): tolerance only, WGSL leaves the order open
+    assert oracle.max_abs_err(got, oracle.wgsl_qgemv_1(x, words, N, K, 2.0)) <= 1e-4
+
+
+def test_qgemv_true_absmax_and_extremes(gpu_ctx, oracle):
+    """Sanity variant with the real absmax, and weights at +-127 (the int8 extremes the codec can emit)."""
+    import wgpu_mm_b200 as w
+    K, N = 256, 512
+    x = oracle.generate_weight_data(23, 1, K)
+    W = oracle.generate_weight_data(24, K, N)
+    W[0, :] = 0.2
+    W[1, :] = -0.2
+    words, absmax = oracle.sint8_quantize(W, K, N)
+    q = words.view(np.int8)
+    assert q.max() == 127 and q.min() == -127
+    prm = w.KernelParams(absmax=absmax, batch=1)
+    got = _run(gpu_ctx, w.KernelId.QGEMV_SINT8, x, words, 1, N, K, prm, b_dtype=np.uint32)
+    e, m = oracle.err_vs_f64(got, oracle.qgemv_f64(x, words, 1, N, K, absmax))
+    assert e / m <= REL_F64
+    # dequantised GEMV approximates the unquantised one to quantisation accuracy
+    full = oracle.mm_f64(x, W)
+    assert np.abs(got - full).max() < 0.05
+
+
+@pytest.mark.parametrize("kid_name", ["QGEMV_SINT8", "QGEMV_1"])
+def test_qgemv_batched(gpu_ctx, oracle, kid_name):
+    """global_id.y batch offsets (qgemv_1.wgsl:12-14) that the reference harness never dispatches."""
+    import wgpu_mm_b200 as w
+    K, N, batch = 256, 512, 3
+    x = oracle.generate_weight_data(25, batch, K)
+    Ws = [oracle.sint8_quantize(oracle.generate_weight_data(30 + b, K, N), K, N)[0] for b in range(batch)]
+    Bq = np.concatenate(Ws)
+    kid = getattr(w.KernelId, kid_name)
+    prm = w.KernelParams(absmax=2.0, batch=batch, workgroup_size=(8, 1, 1) if kid_name == "QGEMV_1" else (0, 0, 0))
+    got = _run(gpu_ctx, kid, x, Bq, 1, N, K, prm, b_dtype=np.uint32)
+    want = oracle.wgsl_qgemv_1(x, Bq, N, K, 2.0, batch=batch)
+    if kid_name == "QGEMV_1":
+        assert np.array_equal(got, want)  # faithful port: bit-exact vs its restatement
+    else:
+        assert oracle.max_abs_err(got, want) <= 1e-4
+    for b in range(batch):
+        assert oracle.max_abs_err(got[b:b + 1], oracle.qgemv_ref(x[b:b + 1], Ws[b], 1, N, K, 2.0)) <= GATE
+
+
+def test_device_datagen_matches_oracle(gpu_ctx, oracle):
+    n = 1 << 16
+    buf = gpu_ctx.buffer(n * 4)
+    for seed, off in ((1, 0), (0x5EED, 12345), (7, 1 << 33)):
+        buf.fill_weights(seed, n, off)
+        got = buf.read(np.float32)
+        want = oracle.generate_weight_data(seed, 1, n, offset=off).reshape(-1)
+        assert np.array_equal(got, want)
+    buf.free()
+
+
+def test_unshard_columns(gpu_ctx):
+    M, N, world = 64, 256, 4
+    full = np.arange(M * N, dtype=np.float32).reshape(M, N)
+    panels = np.concatenate([full[:, r * (N // world):(r + 1) * (N // world)].reshape(-1) for r in range(world)])
+    g = gpu_ctx.buffer_from(panels)
+    c = gpu_ctx.buffer(M * N * 4)
+    gpu_ctx.unshard_columns(g.ptr, c.ptr, M, N, world)
+    assert np.array_equal(c.read(np.float32).reshape(M, N), full)
+    g.free()
+    c.free()
+
+
+def test_launch_rejects_undersized_buffers(gpu_ctx):
+    import wgpu_mm_b200 as w
+    kern = gpu_ctx.kernel(w.KernelId.SGEMM_SIMT, 128, 128, 128)
+    small = gpu_ctx.buffer(16)
+    ok = gpu_ctx.buffer(128 * 128 * 4)
+    with pytest.raises(w.B200mmError):
+        gpu_ctx.launch(kern, small, ok, ok)
+    small.free()
+    ok.free()
+    kern.free()

@@ -1,0 +1,139 @@
+"""CPU tests of the host side: the C ABI loads and exports what include/*.h declares, the C++ host
+mirror (Workload, entry points, codec) behaves like the reference crate, and every compute call fails
+loudly without a GPU (there is no CPU fallback)."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header, macro):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = "\n".join(l for l in text.splitlines() if not l.lstrip().startswith("#"))  # drop the macro definitions
+    return re.findall(macro + r"\s+[^;(]*?\b(\w+)\s*\(", text)
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    names = _declared("b200mm.h", "B200MM_API") + _declared("wgpu_mm_c.h", "WGPUMM_API")
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(built_lib, n), f"{n} declared in include/ but not exported by libb200mm.so"
+
+
+def test_product_never_links_the_oracle(built_lib):
+    import wgpu_mm_b200 as w
+    out = subprocess.run(["nm", "-D", w.lib_path()], capture_output=True, text=True).stdout
+    assert "oracle_" not in out
+    for root, _, files in os.walk(os.path.join(ROOT, "wgpu_mm_b200")):
+        for f in files:
+            if f.endswith((".py", ".cc", ".cu", ".cuh", ".hpp", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert "liboracle" not in src and "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_sass_contains_blackwell_instructions(built_lib):
+    """The tensor-core kernel must really be tcgen05 + TMA (B200_PROFILING.md: UTC*MMA, UTMALDG, LDTM)."""
+    import wgpu_mm_b200 as w
+    sass = subprocess.run(["cuobjdump", "-sass", w.lib_path()], capture_output=True, text=True).stdout
+    assert re.search(r"UTC\w*MMA", sass), "no tcgen05.mma in SASS"
+    assert "UTMALDG" in sass, "no TMA tensor load in SASS"
+    assert "LDTM" in sass, "no tcgen05.ld in SASS"
+    assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", w.lib_path()], capture_output=True, text=True).stdout
+
+
+def test_no_gpu_fails_loudly(built_lib):
+    import wgpu_mm_b200 as w
+    if w.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(w.B200mmError) as e:
+        w.Context(0)
+    assert e.value.code == -3 and "No GPU found" in str(e.value)
+    with pytest.raises(w.B200mmError) as e:
+        w.harness.test_harness(None, "gemm_5", (64, 64, 64), False)
+    assert "No GPU found" in str(e.value)
+
+
+def test_workload_matches_reference_geometry(built_lib):
+    """src/gemm.rs:16-150, src/gemv.rs:17-33 at the crate's shapes."""
+    from wgpu_mm_b200.workload import entry_workload
+    from wgpu_mm_b200 import KernelId
+    expect = {
+        "gemm_1": ((64, 64, 1), (16, 16, 1), KernelId.GEMM_1),
+        "gemm_1v": ((64, 64, 1), (16, 4, 1), KernelId.GEMM_1V),
+        "gemm_2": ((64, 64, 1), (256, 1, 1), KernelId.GEMM_2),
+        "gemm_3": ((64, 64, 1), (256, 1, 1), KernelId.GEMM_3),
+        "gemm_4": ((64, 64, 1), (128, 1, 1), KernelId.GEMM_4),
+        "gemm_5": ((32, 32, 1), (64, 1, 1), KernelId.GEMM_5),
+        "qgemv_1": ((32, 1, 1), (8, 1, 1), KernelId.QGEMV_1),
+        # orphan shaders, geometry inferred in SURVEY 2.2
+        "gemm_wonnx": ((256, 1, 1), (256, 1, 1), KernelId.GEMM_WONNX),
+        "bram8x8": ((64, 32, 1), (4, 8, 1), KernelId.BRAM8X8),
+        "bram": ((32, 32, 1), (8, 8, 1), KernelId.BRAM),
+        "gemm3": ((8, 16, 1), (16, 16, 1), KernelId.GEMM3),
+    }
+    for name, (grid, block, kid) in expect.items():
+        wl, k = entry_workload(name)
+        assert (wl.count.x, wl.count.y, wl.count.z) == grid, name
+        assert (wl.size.x, wl.size.y, wl.size.z) == block, name
+        assert k == kid
+    # x <-> N, y <-> M swap of gemm_4/gemm_5 (src/gemm.rs:109,139)
+    wl, _ = entry_workload("gemm_5", 64, 256, 32)
+    assert (wl.count.x, wl.count.y) == (8, 2)
+
+
+def test_entry_points_fill_the_context(built_lib):
+    from wgpu_mm_b200 import gemm, gemv
+    ctx = {}
+    assert gemm.insert_matrix_dims(ctx) == (1024, 1024, 1024)
+    wl, shader = gemm.gemm_5(ctx)
+    assert shader == "gemm_5" and ctx["workgroup_size_x"] == 64
+    ctx = {}
+    assert gemv.insert_matrix_dims(ctx) == (1, 1024, 1024)
+    assert gemv.ABSMAX == 2.0
+    wl, shader = gemv.qgemv_1(ctx)
+    assert (wl.count.x, wl.size.x) == (32, 8)
+
+
+def test_compute_dim_and_ceil(built_lib, oracle):
+    from wgpu_mm_b200.workload import Workload
+    from wgpu_mm_b200 import B200mmError
+    assert Workload.ceil(1024, 16) == 64 and Workload.ceil(1025, 16) == 65 and Workload.ceil(1, 32) == 1
+    for items in (1, 2, 65535, 65536, 1 << 20, 65535 * 256):
+        assert Workload.compute_dim(items, "X") == oracle.compute_dim(items, "X")
+    with pytest.raises(B200mmError) as e:
+        Workload.compute_dim(65535 * 64 + 1, "Z")
+    assert "Compute limits exceeded" in str(e.value)
+
+
+def test_host_codec_golden_and_vs_oracle(built_lib, oracle):
+    """Product codec (host/quant.cc) vs src/quant.rs:48-64 and vs the oracle, bit for bit."""
+    from wgpu_mm_b200 import quant, B200mmError
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "test_qdq.json")))
+    words, absmax = quant.sint8_quantize(np.array(g["matrix"], dtype=np.float32), 4, 4)
+    assert [int(w) for w in words] == g["words"]
+    deq = quant.sint8_dequantize(words, absmax, 4, 4).reshape(-1)
+    assert np.all(np.abs(np.array(g["matrix"], dtype=np.float32) - deq) < 0.01)
+    for (K, N, seed) in ((4, 4, 1), (64, 256, 2), (128, 1024, 3), (3, 4, 4)):
+        W = oracle.generate_weight_data(seed, K, N)
+        w1, a1 = quant.sint8_quantize(W, K, N)
+        w2, a2 = oracle.sint8_quantize(W, K, N)
+        assert a1 == a2 and np.array_equal(w1, w2)
+        assert np.array_equal(quant.sint8_dequantize(w1, 2.0, K, N), oracle.sint8_dequantize(w2, 2.0, K, N))
+    with pytest.raises(B200mmError):
+        quant.sint8_quantize(np.zeros(6, dtype=np.float32), 2, 3)  # len % 4 != 0 (src/quant.rs:13)
+    with pytest.raises(B200mmError):
+        quant.sint8_quantize(np.zeros(8, dtype=np.float32), 4, 4)  # len != K*N (src/quant.rs:12)
+
+
+def test_cpp_runner_reports_like_cargo(built_lib):
+    exe = os.path.join(ROOT, "wgpu_mm_b200", "lib", "wgpu_mm_tests")
+    assert os.path.exists(exe)
+    r = subprocess.run([exe, "test_qdq"], capture_output=True, text=True)
+    assert r.returncode == 0 and "test test_qdq ... ok" in r.stdout

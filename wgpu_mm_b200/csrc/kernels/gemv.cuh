@@ -1,0 +1,165 @@
+// HBM-streaming GEMV kernels: y[1 x N] = x[1 x K] * W[K x N], W row-major (N contiguous), for
+//   - fp32 weights  (reference semantics: mm_ref with M == 1, src/harness.rs:17-28; there is no fp32
+//                    GEMV shader in the reference), and
+//   - sint8 weights packed 4 per u32 along N in the src/quant.rs:20-26 format, dequantised in registers
+//                   (replaces shaders/gemv/qgemv_1.wgsl:10-39, including its global_id.y batch offsets :12-14).
+//
+// The reference shader gives each invocation 4 outputs and lets it walk all of K serially, so only N/4
+// threads exist and the kernel is latency-bound.  Here the matrix is cut into
+// column panels x K-splits so that >= 2 CTAs per SM each keep UNROLL independent 128-bit loads in
+// flight per thread; a warp covers one contiguous 512 B (or 2 x 256 B) row segment per load, the CTA's
+// warps take interleaved rows, and the K-splits are combined in a FIXED order by the last CTA to
+// finish a panel (atomic ticket), so the result is deterministic run to run.  No tensor cores: the
+// path is bandwidth-bound (algorithmic bytes = weights + x + y).
+//
+// Dequantisation: q in [-127,127] -> float by a byte-permute into the mantissa of 2^23 (1 PRMT +
+// 1 FADD per element; the I2F pipe would be the bottleneck at HBM rate), accumulation of x[k]*q in
+// fp32, and ONE multiply by absmax/127 per output at the end.  The reference multiplies every weight
+// by absmax first (q/127*absmax, src/quant.rs:36-39); factoring the scale out changes the rounding by
+// <= 2 ulp per output, far inside the 1e-3 gate, and is reported against FP64 in the tests.
+#pragma once
+#include "common.cuh"
+
+namespace b200mm {
+
+struct GemvF32 {  // one 128-bit load = 4 columns
+    using Vec = float4;
+    static constexpr int COLS = 4;
+    static __device__ __forceinline__ Vec load(const void* p) { return ldg_stream_f4(reinterpret_cast<const float4*>(p)); }
+    static __device__ __forceinline__ void fma(float (&acc)[COLS], const Vec& w, float xk) {
+        acc[0] = fmaf(xk, w.x, acc[0]);
+        acc[1] = fmaf(xk, w.y, acc[1]);
+        acc[2] = fmaf(xk, w.z, acc[2]);
+        acc[3] = fmaf(xk, w.w, acc[3]);
+    }
+};
+
+struct GemvS8 {  // one 128-bit load = 16 int8 = 16 columns
+    using Vec = uint4;
+    static constexpr int COLS = 16;
+    static __device__ __forceinline__ Vec load(const void* p) { return ldg_stream_u4(reinterpret_cast<const uint4*>(p)); }
+    static __device__ __forceinline__ void fma4(float* acc, uint32_t w, float xk) {
+        // bytes are two's complement; flip the sign bit so each byte is q+128 in [1,255], drop it into the
+        // mantissa of 2^23 and subtract 2^23+128: exact integer -> float without the I2F pipe.
+        const uint32_t u = w ^ 0x80808080u;
+        const float magic = 8388736.0f;  // 2^23 + 128
+        float q0 = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7540)) - magic;
+        float q1 = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7541)) - magic;
+        float q2 = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7542)) - magic;
+        float q3 = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7543)) - magic;
+        acc[0] = fmaf(xk, q0, acc[0]);
+        acc[1] = fmaf(xk, q1, acc[1]);
+        acc[2] = fmaf(xk, q2, acc[2]);
+        acc[3] = fmaf(xk, q3, acc[3]);
+    }
+    static __device__ __forceinline__ void fma(float (&acc)[COLS], const Vec& w, float xk) {
+        fma4(acc + 0, w.x, xk);
+        fma4(acc + 4, w.y, xk);
+        fma4(acc + 8, w.z, xk);
+        fma4(acc + 12, w.w, xk);
+    }
+};
+
+// Launch: grid (panels, splits, batch), block WARPS*32.
+//   LPR   lanes per row segment (32 or 16): a warp reads 32/LPR rows per load instruction
+//   panel = LPR * COLS columns;   rows of a split are dealt round-robin to (warp, row-in-warp) slots.
+// partial: [batch][splits][N] floats, tickets: [batch][panels] u32 (zeroed once; self-resetting).
+template <class T, int WARPS, int UNROLL, int LPR>
+__global__ void __launch_bounds__(WARPS * 32)
+gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, float* __restrict__ y,
+                   float* __restrict__ partial, unsigned int* __restrict__ tickets, int K, int N, int rows_per_split,
+                   float out_scale, size_t x_batch_stride, size_t w_batch_stride_bytes, size_t y_batch_stride) {
+    constexpr int COLS = T::COLS;
+    constexpr int RPW = 32 / LPR;        // rows per warp per load
+    constexpr int RSTEP = WARPS * RPW;   // rows per CTA per load
+    constexpr int PANEL = LPR * COLS;
+    extern __shared__ __align__(16) float sm[];
+    float* xs = sm;                         // rows_per_split floats
+    float* red = sm + rows_per_split;       // WARPS * PANEL floats
+    __shared__ unsigned int s_ticket;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lir = lane % LPR, riw = lane / LPR;
+    const int panel = blockIdx.x, split = blockIdx.y, batch = blockIdx.z, splits = gridDim.y;
+    const int col = panel * PANEL + lir * COLS;
+    const bool col_ok = col < N;  // N % COLS == 0 is required (N % 4 == 0 in the reference)
+
+    x += batch * x_batch_stride;
+    y += batch * y_batch_stride;
+    const char* Wb = reinterpret_cast<const char*>(W) + batch * w_batch_stride_bytes;
+    const size_t row_pitch = (size_t)N / COLS * sizeof(typename T::Vec);  // bytes per weight row
+
+    const int k_beg = split * rows_per_split;
+    const int k_end = min(K, k_beg + rows_per_split);
+    for (int i = tid; i < rows_per_split; i += WARPS * 32) xs[i] = (k_beg + i < k_end) ? x[k_beg + i] : 0.f;
+    __syncthreads();
+
+    float acc[COLS];
+#pragma unroll
+    for (int j = 0; j < COLS; ++j) acc[j] = 0.f;
+
+    const char* wp = Wb + (size_t)col / COLS * sizeof(typename T::Vec);
+    int k = k_beg + warp * RPW + riw;
+    // main loop: UNROLL independent 128-bit loads in flight per thread
+    for (; k + (UNROLL - 1) * RSTEP < k_end; k += UNROLL * RSTEP) {
+        typename T::Vec w[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (col_ok) w[u] = T::load(wp + (size_t)(k + u * RSTEP) * row_pitch);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (col_ok) T::fma(acc, w[u], xs[k + u * RSTEP - k_beg]);
+        }
+    }
+    for (; k < k_end; k += RSTEP) {
+        if (col_ok) {
+            typename T::Vec w = T::load(wp + (size_t)k * row_pitch);
+            T::fma(acc, w, xs[k - k_beg]);
+        }
+    }
+
+    // rows-in-warp -> one partial per column (lanes lir, lir+LPR, ... hold the same columns)
+#pragma unroll
+    for (int off = LPR; off < 32; off <<= 1) {
+#pragma unroll
+        for (int j = 0; j < COLS; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+    }
+    if (riw == 0) {
+#pragma unroll
+        for (int j = 0; j < COLS; ++j) red[warp * PANEL + lir * COLS + j] = acc[j];
+    }
+    __syncthreads();
+
+    // warps -> CTA partial (fixed order), then K-splits (fixed order, by the last CTA of the panel)
+    const size_t pbase = ((size_t)batch * splits) * N;
+    for (int c = tid; c < PANEL; c += WARPS * 32) {
+        const int gc = panel * PANEL + c;
+        if (gc >= N) continue;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) s += red[w * PANEL + c];
+        if (splits == 1)
+            y[gc] = s * out_scale;
+        else
+            partial[pbase + (size_t)split * N + gc] = s;
+    }
+    if (splits == 1) return;
+
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(&tickets[batch * gridDim.x + panel], 1u);
+    __syncthreads();
+    if (s_ticket != (unsigned)splits - 1) return;
+    __threadfence();
+    for (int c = tid; c < PANEL; c += WARPS * 32) {
+        const int gc = panel * PANEL + c;
+        if (gc >= N) continue;
+        float s = 0.f;
+        for (int sp = 0; sp < splits; ++sp) s += __ldcg(&partial[pbase + (size_t)sp * N + gc]);
+        y[gc] = s * out_scale;
+    }
+    if (tid == 0) tickets[batch * gridDim.x + panel] = 0u;  // ready for the next launch
+}
+
+}  // namespace b200mm

@@ -1,0 +1,180 @@
+// Warp-tiled FP32 SGEMM on the FMA pipe (north_star's "accuracy fallback and comparison point").
+//
+// It carries over the idea of the reference's fastest wired shader, shaders/gemm/gemm_5.wgsl:15-86
+// (2-D register tiling: a block tile staged in shared memory, each thread owning a TM x TN patch and
+// doing TM*TN fma per TM+TN shared loads), resized for a B200 SM instead of a 64-thread workgroup:
+//
+//   gemm_5.wgsl            32 x 32 x 16 block tile, 4 x 4 per thread, 64 threads, 2 barriers / k-tile
+//   this kernel           128 x 128 x 16 block tile, 8 x 8 per thread, 256 threads, 1 barrier / k-tile,
+//                          shared memory double-buffered, 128-bit global and shared accesses,
+//                          A staged transposed so both fragments are float4 reads.
+//
+// Accumulation per output is k-sequential fma in fp32, i.e. exactly gemm_5.wgsl's order
+// (threadResults = fma(regM, regN, threadResults), :74-76), so results agree with the
+// oracle_wgsl_gemm_5 restatement bit for bit when K % 16 == 0.
+//
+// Data layout: A (M x K), B (K x N), C (M x N) row-major f32 in HBM; nothing is transposed or padded
+// in global memory.  Shapes that are not multiples of the tile go through the guarded instantiation.
+//
+// Roofline: FMA pipe, 148 SM x 128 lanes x 2 flop x f_clk.  Algorithmic work 2*M*N*K flop.
+#pragma once
+#include "common.cuh"
+
+namespace b200mm {
+
+struct SimtCfg {
+    static constexpr int BM = 128, BN = 128, BK = 16;
+    static constexpr int THREADS = 256;
+    static constexpr int TM = 8, TN = 8;
+    static constexpr int AS_LD = BM + 4;  // padded: transposed stores of A hit different banks
+    static constexpr int BS_LD = BN;
+    static constexpr int SMEM_FLOATS = 2 * (BK * AS_LD + BK * BS_LD);
+};
+
+// Optional fused all-gather: every finished row segment is also stored to the same (row, col) of the
+// full C on each peer GPU (NVLink peer mappings), see b200mm_kernel_set_peers.
+struct PeerStore {
+    float* c[8];
+    int world;     // 0 = disabled
+    int rank;      // own rank: its slot in c[] is the local full C
+    size_t ldc;    // leading dimension of the full C
+    size_t col0;   // first column of this rank's panel in the full C
+};
+
+template <bool GUARD>
+__global__ void __launch_bounds__(SimtCfg::THREADS, 2)
+sgemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K,
+                  int ldc, const __grid_constant__ PeerStore peers) {
+    using Cfg = SimtCfg;
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, AS_LD = Cfg::AS_LD, BS_LD = Cfg::BS_LD;
+    __shared__ __align__(16) float smem[Cfg::SMEM_FLOATS];
+    float* const As0 = smem;                    // As[buf] = As0 + buf * BK * AS_LD   (stored k-major: As[k][m])
+    float* const Bs0 = smem + 2 * BK * AS_LD;   // Bs[buf] = Bs0 + buf * BK * BS_LD   (Bs[k][n])
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    // 8 warps as 2 (m) x 4 (n); warp tile 64 x 32; lanes as 8 (m) x 4 (n); thread patch = 2 x 2 blocks of 4 x 4
+    const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+    const int tm = (lane >> 2) * 4, tn = (lane & 3) * 4;
+
+    // consecutive blockIdx.x walk down M inside a 128-column panel of B so that panel stays L2/L1-hot
+    const int block_m = blockIdx.x * BM, block_n = blockIdx.y * BN;
+
+    // global -> register staging: A tile 128 x 16 = 512 float4 (2 per thread), B tile 16 x 128 = 512 float4
+    const int a_row = tid >> 2, a_kq = (tid & 3) * 4;  // rows a_row and a_row + 64
+    const int b_row = tid >> 5, b_col = (tid & 31) * 4;  // rows b_row and b_row + 8
+    const float* Ag = A + (size_t)(block_m + a_row) * K + a_kq;
+    const float* Bg = B + (size_t)b_row * N + block_n + b_col;
+
+    float4 ra[2], rb[2];
+    auto load_tile = [&](int k0) {
+        if constexpr (!GUARD) {
+            ra[0] = __ldg(reinterpret_cast<const float4*>(Ag + k0));
+            ra[1] = __ldg(reinterpret_cast<const float4*>(Ag + (size_t)64 * K + k0));
+            rb[0] = __ldg(reinterpret_cast<const float4*>(Bg + (size_t)k0 * N));
+            rb[1] = __ldg(reinterpret_cast<const float4*>(Bg + (size_t)(k0 + 8) * N));
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float v[4];
+                const int r = block_m + a_row + 64 * h;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = k0 + a_kq + j;
+                    v[j] = (r < M && k < K) ? A[(size_t)r * K + k] : 0.f;
+                }
+                ra[h] = make_float4(v[0], v[1], v[2], v[3]);
+                const int kb = k0 + b_row + 8 * h;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = block_n + b_col + j;
+                    v[j] = (kb < K && c < N) ? B[(size_t)kb * N + c] : 0.f;
+                }
+                rb[h] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+    };
+    auto store_tile = [&](int buf) {
+        float* as = As0 + buf * (BK * AS_LD);
+        float* bs = Bs0 + buf * (BK * BS_LD);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = a_row + 64 * h;
+            as[(a_kq + 0) * AS_LD + r] = ra[h].x;
+            as[(a_kq + 1) * AS_LD + r] = ra[h].y;
+            as[(a_kq + 2) * AS_LD + r] = ra[h].z;
+            as[(a_kq + 3) * AS_LD + r] = ra[h].w;
+            *reinterpret_cast<float4*>(&bs[(b_row + 8 * h) * BS_LD + b_col]) = rb[h];
+        }
+    };
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    const int KT = (K + BK - 1) / BK;
+    load_tile(0);
+    store_tile(0);
+    __syncthreads();
+
+    for (int kt = 0; kt < KT; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < KT) load_tile((kt + 1) * BK);  // global loads in flight across the whole k-tile
+        const float* as = As0 + buf * (BK * AS_LD) + wm + tm;
+        const float* bs = Bs0 + buf * (BK * BS_LD) + wn + tn;
+        float4 fa[2][2], fb[2][2];  // register double buffer for the fragments
+        fa[0][0] = *reinterpret_cast<const float4*>(as);
+        fa[0][1] = *reinterpret_cast<const float4*>(as + 32);
+        fb[0][0] = *reinterpret_cast<const float4*>(bs);
+        fb[0][1] = *reinterpret_cast<const float4*>(bs + 16);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const int cur = k & 1, nxt = cur ^ 1;
+            if (k + 1 < BK) {
+                fa[nxt][0] = *reinterpret_cast<const float4*>(as + (k + 1) * AS_LD);
+                fa[nxt][1] = *reinterpret_cast<const float4*>(as + (k + 1) * AS_LD + 32);
+                fb[nxt][0] = *reinterpret_cast<const float4*>(bs + (k + 1) * BS_LD);
+                fb[nxt][1] = *reinterpret_cast<const float4*>(bs + (k + 1) * BS_LD + 16);
+            }
+            const float a[8] = {fa[cur][0].x, fa[cur][0].y, fa[cur][0].z, fa[cur][0].w,
+                                fa[cur][1].x, fa[cur][1].y, fa[cur][1].z, fa[cur][1].w};
+            const float b[8] = {fb[cur][0].x, fb[cur][0].y, fb[cur][0].z, fb[cur][0].w,
+                                fb[cur][1].x, fb[cur][1].y, fb[cur][1].z, fb[cur][1].w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kt + 1 < KT) store_tile(buf ^ 1);
+        __syncthreads();
+    }
+
+    // epilogue: rows {tm..tm+3, 32+tm..}, cols {tn..tn+3, 16+tn..} of the warp tile; float4 stores
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = block_m + wm + tm + (i & 3) + (i >> 2) * 32;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = block_n + wn + tn + h * 16;
+            const float4 v = make_float4(acc[i][4 * h + 0], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]);
+            if constexpr (!GUARD) {
+                if (peers.world == 0) {
+                    *reinterpret_cast<float4*>(&C[(size_t)r * ldc + c]) = v;
+                } else {
+#pragma unroll 1
+                    for (int p = 0; p < peers.world; ++p)
+                        *reinterpret_cast<float4*>(&peers.c[p][(size_t)r * peers.ldc + peers.col0 + c]) = v;
+                }
+            } else {
+                const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (r < M && c + j < N) C[(size_t)r * ldc + c + j] = e[j];
+            }
+        }
+    }
+}
+
+}  // namespace b200mm

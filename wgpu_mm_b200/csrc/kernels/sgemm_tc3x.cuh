@@ -1,0 +1,368 @@
+// FP32-accurate SGEMM on the 5th-generation tensor cores: TMA -> shared memory -> tcgen05.mma
+// (kind::tf32) -> TMEM accumulators -> tcgen05.ld epilogue, with the 3xTF32 split
+//
+//     x = hi + lo,  hi = tf32(x) (round to nearest),  lo = tf32(x - hi)
+//     A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi        (the lo*lo term is below fp32 resolution)
+//
+// This is north_star's main SGEMM kernel; it replaces the register-tiled WGSL shaders
+// (shaders/gemm/gemm_5.wgsl:15-86 and the orphan bram/gemm3 kernels) for C = A*B with
+// A (M x K), B (K x N), C (M x N) row-major f32 (src/harness.rs:17-28 fixes the layout).
+//
+// Two kernels per GEMM:
+//   1. split_tf32_kernel   elementwise pass, HBM-bound: reads A and B once, writes A_hi, A_lo, B_hi, B_lo
+//                          (kind::tf32 ignores the low 13 mantissa bits of its 32-bit operands, so hi and lo
+//                          must be materialised as exactly-representable tf32 values);
+//   2. sgemm_tc3x_kernel   persistent, warp-specialised:
+//        warp 0    TMA producer: per k-block loads A_hi/A_lo (128 x 32, K-major, SWIZZLE_128B) and
+//                  B_hi/B_lo (32 x BN, N-major: B is K x N row-major, so it is consumed as an MN-major
+//                  operand straight from its natural layout -- no transpose anywhere)
+//        warp 1    MMA issuer: one elected thread issues 3 x (BK/8) tcgen05.mma per k-block into a
+//                  128 x BN fp32 accumulator in TMEM; tcgen05.commit releases the smem stage
+//        warp 2    TMEM allocator
+//        warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> float4 stores to C
+//                  (and, for the N-sharded multi-GPU path, to the same tile of C on every peer GPU)
+//      The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
+//      the main loop of tile i+1.
+//
+// Roofline: tensor pipe.  Algorithmic work 2*M*N*K flop; the tensor pipe executes 3x that in TF32.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "sgemm_simt.cuh"  // PeerStore
+
+namespace b200mm {
+
+// ------------------------------------------------------------------------------------------------
+// operand split
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__global__ void split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo,
+                                  size_t n4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n4; i += stride) {
+        const float4 v = __ldg(x + i);
+        float4 h, l;
+        h.x = to_tf32_rna(v.x); l.x = to_tf32_rna(v.x - h.x);
+        h.y = to_tf32_rna(v.y); l.y = to_tf32_rna(v.y - h.y);
+        h.z = to_tf32_rna(v.z); l.z = to_tf32_rna(v.z - h.z);
+        h.w = to_tf32_rna(v.w); l.w = to_tf32_rna(v.w - h.w);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ------------------------------------------------------------------------------------------------
+namespace ptx {
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], tf32 inputs, fp32 accumulate; one thread issues for the CTA.
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, float (&v)[32]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+}  // namespace ptx
+
+// ------------------------------------------------------------------------------------------------
+// descriptors
+// ------------------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor (tcgen05): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), base_offset [49,52)=0, layout [61,64): 2 = SWIZZLE_128B.
+__host__ __device__ constexpr uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// Instruction descriptor, kind::tf32: D=f32 [4,6)=1, A fmt [7,10)=2 (tf32), B fmt [10,13)=2,
+// A major bit15 (0 = K-major), B major bit16 (1 = MN-major), N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n, bool a_mn_major, bool b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct Tc3xArgs {
+    float* C;
+    int M, N, K, ldc;
+    int tiles_m, tiles_n;
+    PeerStore peers;
+};
+
+template <int BN_, int STAGES_, bool ONE_PASS_>
+struct Tc3xCfg {
+    static constexpr int BM = 128, BN = BN_, BK = 32, STAGES = STAGES_;
+    static constexpr bool ONE_PASS = ONE_PASS_;
+    static constexpr int THREADS = 256;
+    static constexpr uint32_t A_BYTES = BM * BK * 4;           // 16 KiB, 128 rows x 128 B, SW128 K-major
+    static constexpr uint32_t B_BYTES = BK * BN * 4;           // BN/32 atoms x (32 k-rows x 128 B), SW128 MN-major
+    static constexpr uint32_t STAGE_BYTES = (ONE_PASS ? 1 : 2) * (A_BYTES + B_BYTES);
+    static constexpr uint32_t TMEM_COLS = 2 * BN;              // double-buffered fp32 accumulator
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM cols: power of 2");
+};
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ Tc3xArgs p) {
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
+    constexpr bool ONE_PASS = Cfg::ONE_PASS;
+    constexpr uint32_t A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms are 1024 B aligned
+    const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    auto sA_hi = [&](int s) { return smem_base + s * STAGE_BYTES; };
+    auto sA_lo = [&](int s) { return smem_base + s * STAGE_BYTES + A_BYTES; };
+    auto sB_hi = [&](int s) { return smem_base + s * STAGE_BYTES + (ONE_PASS ? 1 : 2) * A_BYTES; };
+    auto sB_lo = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * A_BYTES + B_BYTES; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int num_kb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmAh);
+        ptx::prefetch_tmap(&tmBh);
+        if (!ONE_PASS) {
+            ptx::prefetch_tmap(&tmAl);
+            ptx::prefetch_tmap(&tmBl);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(tfull_bar(s), 1);
+            ptx::mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    // tile order: m fastest, so the CTAs of one wave share a few B column panels and stream A
+    auto tile_coords = [&](int t, int& tm, int& tn) {
+        tm = t % p.tiles_m;
+        tn = t / p.tiles_m;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                int tm, tn;
+                tile_coords(t, tm, tn);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+                    ptx::tma_load_2d(sA_hi(stage), &tmAh, full_bar(stage), kb * BK, tm * BM);
+                    ptx::tma_load_3d(sB_hi(stage), &tmBh, full_bar(stage), 0, kb * BK, tn * (BN / 32));
+                    if (!ONE_PASS) {
+                        ptx::tma_load_2d(sA_lo(stage), &tmAl, full_bar(stage), kb * BK, tm * BM);
+                        ptx::tma_load_3d(sB_lo(stage), &tmBl, full_bar(stage), 0, kb * BK, tn * (BN / 32));
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(BM, BN, /*A MN-major*/ false, /*B MN-major*/ true);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                ptx::mbar_wait(tempty_bar(as), aphase ^ 1);  // epilogue has drained this accumulator
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(full_bar(stage), phase);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int j = 0; j < BK / 8; ++j) {
+                        // A (K-major SW128): 8 tf32 = 32 B along the swizzled row; SBO = 8 rows x 128 B
+                        const uint64_t a_hi = make_smem_desc_sw128(sA_hi(stage) + j * 32, 16, 1024);
+                        // B (MN-major SW128): one 8-deep k-group = 1024 B; LBO = stride between 32-column atoms
+                        const uint64_t b_hi = make_smem_desc_sw128(sB_hi(stage) + j * 1024, BK * 128, 1024);
+                        const uint32_t acc0 = (kb > 0 || j > 0) ? 1u : 0u;
+                        if (!ONE_PASS) {
+                            const uint64_t a_lo = make_smem_desc_sw128(sA_lo(stage) + j * 32, 16, 1024);
+                            const uint64_t b_lo = make_smem_desc_sw128(sB_lo(stage) + j * 1024, BK * 128, 1024);
+                            ptx::mma_tf32_ss(d_tmem, a_lo, b_hi, idesc, acc0);  // small terms first
+                            ptx::mma_tf32_ss(d_tmem, a_hi, b_lo, idesc, 1u);
+                            ptx::mma_tf32_ss(d_tmem, a_hi, b_hi, idesc, 1u);
+                        } else {
+                            ptx::mma_tf32_ss(d_tmem, a_hi, b_hi, idesc, acc0);
+                        }
+                    }
+                    ptx::mma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                ptx::mma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (warps 4..7 <-> TMEM lanes 32*(warp%4) ..) =====================
+        const int q = warp & 3;
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            int tm, tn;
+            tile_coords(t, tm, tn);
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            ptx::mbar_wait(tfull_bar(as), aphase);
+            ptx::tc_fence_after();
+            const int row = tm * BM + q * 32 + lane;
+            const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                float v[32];
+                ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+                ptx::tmem_ld_wait();
+                const int col = tn * BN + c * 32;
+                if (row < p.M) {
+                    if (p.peers.world == 0) {
+                        float* dst = p.C + (size_t)row * p.ldc + col;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (col + 4 * j < p.N)
+                                *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+#pragma unroll 1
+                        for (int pr = 0; pr < p.peers.world; ++pr) {
+                            float* dst = p.peers.c[pr] + (size_t)row * p.peers.ldc + p.peers.col0 + col;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (col + 4 * j < p.N)
+                                    *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace b200mm
