@@ -132,6 +132,11 @@ B200MM_API int b200mm_host_free(void* p);
  * src/harness.rs:103-121 with a seed added): fills n f32 starting at stream position `offset`. */
 B200MM_API int b200mm_buffer_fill_weights(b200mm_ctx* ctx, b200mm_buffer* buf, uint64_t seed, uint64_t offset, size_t n);
 
+/* Same stream, for a column panel of a row-major matrix with leading dimension src_ld: element (r, c) of the
+ * rows x cols buffer receives stream position offset + r*src_ld + src_col0 + c (N-sharded B panels). */
+B200MM_API int b200mm_buffer_fill_weights_2d(b200mm_ctx* ctx, b200mm_buffer* buf, uint64_t seed, uint64_t offset, size_t rows,
+                                             size_t cols, size_t src_ld, size_t src_col0);
+
 /* ---- kernels: shader module + pipeline, src/harness.rs:179-191 -------------------------------- */
 /* Shapes are fixed per kernel object exactly as they are baked into the reference's WGSL
  * (src/gemm.rs:5-7).  May allocate device workspace (split operands, split-K partials). */

@@ -124,6 +124,7 @@ def _declare(l: C.CDLL) -> None:
     l.b200mm_host_alloc.argtypes = [sz, C.POINTER(vp)]
     l.b200mm_host_free.argtypes = [vp]
     l.b200mm_buffer_fill_weights.argtypes = [vp, vp, C.c_uint64, C.c_uint64, sz]
+    l.b200mm_buffer_fill_weights_2d.argtypes = [vp, vp, C.c_uint64, C.c_uint64, sz, sz, sz, sz]
     l.b200mm_kernel_get.argtypes = [vp, C.c_int, sz, sz, sz, C.POINTER(KernelParamsC), C.POINTER(vp)]
     l.b200mm_kernel_free.argtypes = [vp, vp]
     l.b200mm_kernel_name.restype = C.c_char_p

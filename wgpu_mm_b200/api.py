@@ -165,6 +165,9 @@ class Buffer:
     def fill_weights(self, seed: int, n: int, offset: int = 0):
         check(lib().b200mm_buffer_fill_weights(self.ctx.handle, self._h, seed, offset, n), self.ctx.handle)
 
+    def fill_weights_2d(self, seed: int, rows: int, cols: int, src_ld: int, src_col0: int, offset: int = 0):
+        check(lib().b200mm_buffer_fill_weights_2d(self.ctx.handle, self._h, seed, offset, rows, cols, src_ld, src_col0), self.ctx.handle)
+
     def ipc_export(self) -> bytes:
         hb = C.create_string_buffer(64)
         check(lib().b200mm_ipc_export(self.ctx.handle, self._h, hb), self.ctx.handle)

@@ -19,6 +19,7 @@
 #include "kernels/sgemm_simt.cuh"
 #include "kernels/sgemm_tc3x.cuh"
 #include "kernels/wgsl_ports.cuh"
+#include "kernels/tc_probe.cuh"
 
 using namespace b200mm;
 
@@ -279,6 +280,19 @@ extern "C" int b200mm_buffer_fill_weights(b200mm_ctx* ctx, b200mm_buffer* buf, u
     return B200MM_OK;
 }
 
+extern "C" int b200mm_buffer_fill_weights_2d(b200mm_ctx* ctx, b200mm_buffer* buf, uint64_t seed, uint64_t offset, size_t rows,
+                                             size_t cols, size_t src_ld, size_t src_col0) {
+    if (!ctx || !buf) return fail(ctx, B200MM_ERR_INVALID, "fill_weights_2d: NULL argument");
+    if (rows * cols * sizeof(float) > buf->bytes) return fail(ctx, B200MM_ERR_INVALID, "fill_weights_2d: range exceeds buffer");
+    if (src_col0 + cols > src_ld) return fail(ctx, B200MM_ERR_INVALID, "fill_weights_2d: panel exceeds the source row");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const int blocks = (int)std::min<size_t>(ceil_div(rows * cols, 256), (size_t)ctx->prop.multiProcessorCount * 16);
+    fill_weights_2d_kernel<<<std::max(blocks, 1), 256, 0, ctx->stream>>>((float*)buf->ptr, seed, offset, rows, cols, src_ld, src_col0);
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return B200MM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // TMA descriptors (driver entry point fetched through the runtime: no link-time libcuda dependency)
 // ------------------------------------------------------------------------------------------------
@@ -316,7 +330,7 @@ static int make_tmap_kmajor(b200mm_ctx* ctx, CUtensorMap* tm, const float* base,
 // B operand: row-major K x N f32 consumed MN-major.  Viewed as 3-D (n%32, k, n/32) so that one TMA
 // box lands [n/32][k][32] = the canonical SWIZZLE_128B MN-major atoms in shared memory.
 static int make_tmap_mnmajor(b200mm_ctx* ctx, CUtensorMap* tm, const float* base, size_t K, size_t N, int box_k,
-                             int box_n) {
+                             int box_n, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return fail(ctx, B200MM_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
     cuuint64_t dims[3] = {32, K, ceil_div(N, 32)};
@@ -324,7 +338,7 @@ static int make_tmap_mnmajor(b200mm_ctx* ctx, CUtensorMap* tm, const float* base
     cuuint32_t box[3] = {32, (cuuint32_t)box_k, (cuuint32_t)(box_n / 32)};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, B200MM_ERR_CUDA, "cuTensorMapEncodeTiled(MN-major) failed: %d", (int)r);
     return B200MM_OK;
@@ -506,7 +520,7 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     }
     const int tiles = (int)(ceil_div(M, 128) * ceil_div(N, k->tc_bn));
     k->grid = dim3(std::min(tiles, ctx->prop.multiProcessorCount), 1, 1);
-    k->block = dim3(256, 1, 1);
+    k->block = dim3(Tc256::THREADS, 1, 1);
     if (one_pass) {
         k->smem = Tc256x1::SMEM_BYTES;
         CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc256x1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
@@ -882,5 +896,30 @@ extern "C" int b200mm_unshard_columns(b200mm_ctx* ctx, const void* gathered, voi
     unshard_columns_kernel<<<ctx->prop.multiProcessorCount * 8, 256, 0, ctx->stream>>>((const float4*)gathered, (float4*)C, M, N / 4, world);
     CU_TRY(ctx, cudaGetLastError());
     ctx->launches++;
+    return B200MM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// debug: tcgen05 bring-up probe (tools/probe_tc.py); not part of the public header
+// ------------------------------------------------------------------------------------------------
+extern "C" B200MM_API int b200mm_debug_tc_probe(b200mm_ctx* ctx, const void* A, const void* B, size_t M, size_t N, size_t K,
+                                                const uint32_t* u32args /*11*/, void* dumpA, void* dumpB, void* dumpD) {
+    if (!ctx || !A || !B) return fail(ctx, B200MM_ERR_INVALID, "probe: NULL argument");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CUtensorMap tmA, tmB;
+    int rc;
+    if ((rc = make_tmap_kmajor(ctx, &tmA, (const float*)A, M, K, 128))) return rc;
+    if ((rc = make_tmap_mnmajor(ctx, &tmB, (const float*)B, K, N, 32, 256, (CUtensorMapSwizzle)u32args[10]))) return rc;
+    ProbeArgs pa{};
+    pa.idesc = u32args[0];
+    pa.a_lbo = u32args[1]; pa.a_sbo = u32args[2]; pa.a_kstep = u32args[3];
+    pa.b_lbo = u32args[4]; pa.b_sbo = u32args[5]; pa.b_kstep = u32args[6];
+    pa.layout = u32args[7]; pa.nk = u32args[8]; pa.mode = u32args[9];
+    pa.dumpA = (float*)dumpA; pa.dumpB = (float*)dumpB; pa.dumpD = (float*)dumpD;
+    const int smem = 128 * 32 * 4 + 32 * 256 * 4 + 1024 + 256;
+    CU_TRY(ctx, cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tc_probe_kernel<<<1, 256, smem, ctx->stream>>>(tmA, tmB, pa);
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return B200MM_OK;
 }

@@ -26,6 +26,16 @@ __global__ void fill_weights_kernel(float* __restrict__ out, uint64_t seed, uint
     for (; i < n; i += stride) out[i] = weight_value(seed, offset + i);
 }
 
+__global__ void fill_weights_2d_kernel(float* __restrict__ out, uint64_t seed, uint64_t offset, size_t rows, size_t cols,
+                                       size_t src_ld, size_t src_col0) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, n = rows * cols;
+    for (; i < n; i += stride) {
+        const size_t r = i / cols, c = i % cols;
+        out[i] = weight_value(seed, offset + r * src_ld + src_col0 + c);
+    }
+}
+
 // [world][M][N/world] -> row-major M x N (after an all-gather of column panels).
 __global__ void unshard_columns_kernel(const float4* __restrict__ gathered, float4* __restrict__ C, size_t M,
                                        size_t n4, int world) {

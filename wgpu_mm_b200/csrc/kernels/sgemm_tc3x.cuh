@@ -15,14 +15,17 @@
 //   2. sgemm_tc3x_kernel   persistent, warp-specialised:
 //        warp 0    TMA producer: per k-block loads A_hi/A_lo (128 x 32, K-major, SWIZZLE_128B) and
 //                  B_hi/B_lo (32 x BN, N-major: B is K x N row-major, so it is consumed as an MN-major
-//                  operand straight from its natural layout -- no transpose anywhere)
+//                  operand straight from its natural layout -- no transpose anywhere; a 3-D tensor map
+//                  (n%32, k, n/32) with SWIZZLE_128B_ATOM_32B lands the canonical MN-major atoms)
 //        warp 1    MMA issuer: one elected thread issues 3 x (BK/8) tcgen05.mma per k-block into a
 //                  128 x BN fp32 accumulator in TMEM; tcgen05.commit releases the smem stage
 //        warp 2    TMEM allocator
-//        warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> float4 stores to C
-//                  (and, for the N-sharded multi-GPU path, to the same tile of C on every peer GPU)
-//      The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
-//      the main loop of tile i+1.
+//        warps 4-11 epilogue (two warpgroups, one per column half): after every CHAIN k-blocks tcgen05.ld the
+//                  finished chain from TMEM and fold it into fp32 register accumulators with round-to-nearest
+//                  adds (the tensor core's own accumulation truncates); at the end of the tile float4 stores
+//                  to C (and, for the N-sharded multi-GPU path, to the same tile of C on every peer GPU)
+//      Two chain accumulators ping-pong in TMEM (2 x BN columns), so folding chain i overlaps the MMAs of
+//      chain i+1, across tile boundaries as well.
 //
 // Roofline: tensor pipe.  Algorithmic work 2*M*N*K flop; the tensor pipe executes 3x that in TF32.
 #pragma once
@@ -155,10 +158,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // descriptors
 // ------------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (tcgen05): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
-// version=1 [46,48), base_offset [49,52)=0, layout [61,64): 2 = SWIZZLE_128B.
-__host__ __device__ constexpr uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// version=1 [46,48), base_offset [49,52)=0, layout [61,64).
+//   layout 2 = SWIZZLE_128B          16-byte chunks XOR (row % 8); 8-row atoms.  Used for the K-major A tiles.
+//   layout 1 = SWIZZLE_128B_BASE32B  32-byte chunks XOR (row % 4); 4-row atoms.  The ONLY layout the tensor core
+//                                    accepts for MN-major 32-bit (tf32) operands -- with layout 2 the MMA silently
+//                                    produces zeros (measured, tools/probe_tc.py).  TMA side: SWIZZLE_128B_ATOM_32B.
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32B = 1;
+__host__ __device__ constexpr uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(layout & 7u) << 61);
 }
 // Instruction descriptor, kind::tf32: D=f32 [4,6)=1, A fmt [7,10)=2 (tf32), B fmt [10,13)=2,
 // A major bit15 (0 = K-major), B major bit16 (1 = MN-major), N>>3 [17,23), M>>4 [24,29).
@@ -174,29 +182,37 @@ struct Tc3xArgs {
     PeerStore peers;
 };
 
-template <int BN_, int STAGES_, bool ONE_PASS_>
+// CHAIN: number of k-blocks accumulated inside TMEM before the partial sum is folded into fp32 registers.
+// Measured on B200 (tools/debug_tc3x.py): the tensor core adds into its fp32 accumulator with truncation, so a
+// single chain over K = 4096 (1536 accumulate steps) is biased by ~1e-4 -- 10x worse than a sequential fp32 loop.
+// Chains of 8 k-blocks (256 k, 96 steps) folded with round-to-nearest FADDs bring the error back to the fp32 level.
+template <int BN_, int STAGES_, bool ONE_PASS_, int CHAIN_ = 8>
 struct Tc3xCfg {
-    static constexpr int BM = 128, BN = BN_, BK = 32, STAGES = STAGES_;
+    static constexpr int BM = 128, BN = BN_, BK = 32, STAGES = STAGES_, CHAIN = CHAIN_;
     static constexpr bool ONE_PASS = ONE_PASS_;
-    static constexpr int THREADS = 256;
-    static constexpr uint32_t A_BYTES = BM * BK * 4;           // 16 KiB, 128 rows x 128 B, SW128 K-major
-    static constexpr uint32_t B_BYTES = BK * BN * 4;           // BN/32 atoms x (32 k-rows x 128 B), SW128 MN-major
+    static constexpr int EPI_WARPS = 8;                        // two warpgroups, each owns half of the BN columns
+    static constexpr int THREADS = 128 + EPI_WARPS * 32;       // warps 0-3: TMA / MMA / TMEM alloc / idle
+    static constexpr int COLS_PER_WG = BN / 2;
+    static constexpr uint32_t A_BYTES = BM * BK * 4;           // 16 KiB, 128 rows x 128 B, SWIZZLE_128B, K-major
+    static constexpr uint32_t B_BYTES = BK * BN * 4;           // BN/32 atoms x (32 k-rows x 128 B), SWIZZLE_128B_BASE32B, MN-major
     static constexpr uint32_t STAGE_BYTES = (ONE_PASS ? 1 : 2) * (A_BYTES + B_BYTES);
-    static constexpr uint32_t TMEM_COLS = 2 * BN;              // double-buffered fp32 accumulator
+    static constexpr uint32_t TMEM_COLS = 2 * BN;              // two chain accumulators (ping-pong)
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM cols: power of 2");
+    static_assert(COLS_PER_WG % 32 == 0, "epilogue reads 32 columns per tcgen05.ld");
 };
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ Tc3xArgs p) {
-    constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
+                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                  const __grid_constant__ Tc3xArgs p) {
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, CHAIN = Cfg::CHAIN;
     constexpr bool ONE_PASS = Cfg::ONE_PASS;
     constexpr uint32_t A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
 
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms are 1024 B aligned
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms are 1024 B aligned
     const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -227,7 +243,7 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(tfull_bar(s), 1);
-            ptx::mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+            ptx::mbar_init(tempty_bar(s), Cfg::EPI_WARPS);  // one arrive per epilogue warp
         }
         ptx::fence_barrier_init();
     }
@@ -247,113 +263,128 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         tn = t / p.tiles_m;
     };
 
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                int tm, tn;
-                tile_coords(t, tm, tn);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    ptx::mbar_wait(empty_bar(stage), phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-                    ptx::tma_load_2d(sA_hi(stage), &tmAh, full_bar(stage), kb * BK, tm * BM);
-                    ptx::tma_load_3d(sB_hi(stage), &tmBh, full_bar(stage), 0, kb * BK, tn * (BN / 32));
-                    if (!ONE_PASS) {
-                        ptx::tma_load_2d(sA_lo(stage), &tmAl, full_bar(stage), kb * BK, tm * BM);
-                        ptx::tma_load_3d(sB_lo(stage), &tmBl, full_bar(stage), 0, kb * BK, tn * (BN / 32));
-                    }
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(BM, BN, /*A MN-major*/ false, /*B MN-major*/ true);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-                const int as = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                ptx::mbar_wait(tempty_bar(as), aphase ^ 1);  // epilogue has drained this accumulator
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    ptx::mbar_wait(full_bar(stage), phase);
-                    ptx::tc_fence_after();
-#pragma unroll
-                    for (int j = 0; j < BK / 8; ++j) {
-                        // A (K-major SW128): 8 tf32 = 32 B along the swizzled row; SBO = 8 rows x 128 B
-                        const uint64_t a_hi = make_smem_desc_sw128(sA_hi(stage) + j * 32, 16, 1024);
-                        // B (MN-major SW128): one 8-deep k-group = 1024 B; LBO = stride between 32-column atoms
-                        const uint64_t b_hi = make_smem_desc_sw128(sB_hi(stage) + j * 1024, BK * 128, 1024);
-                        const uint32_t acc0 = (kb > 0 || j > 0) ? 1u : 0u;
+    if (warp < 4) {
+        if (warp == 0) {
+            // ===================== TMA producer =====================
+            if (lane == 0) {
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                    int tm, tn;
+                    tile_coords(t, tm, tn);
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+                        ptx::mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+                        ptx::tma_load_2d(sA_hi(stage), &tmAh, full_bar(stage), kb * BK, tm * BM);
+                        ptx::tma_load_3d(sB_hi(stage), &tmBh, full_bar(stage), 0, kb * BK, tn * (BN / 32));
                         if (!ONE_PASS) {
-                            const uint64_t a_lo = make_smem_desc_sw128(sA_lo(stage) + j * 32, 16, 1024);
-                            const uint64_t b_lo = make_smem_desc_sw128(sB_lo(stage) + j * 1024, BK * 128, 1024);
-                            ptx::mma_tf32_ss(d_tmem, a_lo, b_hi, idesc, acc0);  // small terms first
-                            ptx::mma_tf32_ss(d_tmem, a_hi, b_lo, idesc, 1u);
-                            ptx::mma_tf32_ss(d_tmem, a_hi, b_hi, idesc, 1u);
-                        } else {
-                            ptx::mma_tf32_ss(d_tmem, a_hi, b_hi, idesc, acc0);
+                            ptx::tma_load_2d(sA_lo(stage), &tmAl, full_bar(stage), kb * BK, tm * BM);
+                            ptx::tma_load_3d(sB_lo(stage), &tmBl, full_bar(stage), 0, kb * BK, tn * (BN / 32));
+                        }
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
                         }
                     }
-                    ptx::mma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
+                }
+            }
+        } else if (warp == 1) {
+            // ===================== MMA issuer =====================
+            if (lane == 0) {
+                constexpr uint32_t idesc = make_idesc_tf32(BM, BN, /*A MN-major*/ false, /*B MN-major*/ true);
+                int stage = 0;
+                uint32_t phase = 0;
+                uint32_t chain = 0;  // running chain index: TMEM buffer = chain & 1
+                for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                    for (int kb0 = 0; kb0 < num_kb; kb0 += CHAIN, ++chain) {
+                        const uint32_t as = chain & 1, aphase = (chain >> 1) & 1;
+                        ptx::mbar_wait(tempty_bar(as), aphase ^ 1);  // epilogue has drained this accumulator
+                        ptx::tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + as * BN;
+                        const int kb1 = min(kb0 + CHAIN, num_kb);
+                        for (int kb = kb0; kb < kb1; ++kb) {
+                            ptx::mbar_wait(full_bar(stage), phase);
+                            ptx::tc_fence_after();
+#pragma unroll
+                            for (int j = 0; j < BK / 8; ++j) {
+                                // A (K-major, SWIZZLE_128B): 8 tf32 = 32 B along the swizzled row; SBO = 8 rows x 128 B
+                                const uint64_t a_hi = make_smem_desc(sA_hi(stage) + j * 32, 16, 1024, kLayoutSw128);
+                                // B (MN-major, SWIZZLE_128B_BASE32B): 8 k-rows = two 4-row atoms (SBO = 512 B) per MMA;
+                                // LBO = stride between 32-column atoms = BK rows x 128 B
+                                const uint64_t b_hi = make_smem_desc(sB_hi(stage) + j * 1024, BK * 128, 512, kLayoutSw128Base32B);
+                                const uint32_t acc0 = (kb > kb0 || j > 0) ? 1u : 0u;  // first MMA of a chain overwrites
+                                if (!ONE_PASS) {
+                                    const uint64_t a_lo = make_smem_desc(sA_lo(stage) + j * 32, 16, 1024, kLayoutSw128);
+                                    const uint64_t b_lo = make_smem_desc(sB_lo(stage) + j * 1024, BK * 128, 512, kLayoutSw128Base32B);
+                                    ptx::mma_tf32_ss(d_tmem, a_lo, b_hi, idesc, acc0);  // small terms first
+                                    ptx::mma_tf32_ss(d_tmem, a_hi, b_lo, idesc, 1u);
+                                    ptx::mma_tf32_ss(d_tmem, a_hi, b_hi, idesc, 1u);
+                                } else {
+                                    ptx::mma_tf32_ss(d_tmem, a_hi, b_hi, idesc, acc0);
+                                }
+                            }
+                            ptx::mma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
+                            if (++stage == STAGES) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                        ptx::mma_commit(tfull_bar(as));  // chain complete -> epilogue
                     }
                 }
-                ptx::mma_commit(tfull_bar(as));  // accumulator complete -> epilogue
             }
         }
-    } else if (warp >= 4) {
-        // ===================== epilogue (warps 4..7 <-> TMEM lanes 32*(warp%4) ..) =====================
+    } else {
+        // ===================== epilogue: 2 warpgroups x 4 warps =====================
+        // warp % 4 selects the TMEM lane quadrant (hardware restriction), the warpgroup selects the column half.
+        constexpr int COLS = Cfg::COLS_PER_WG;
         const int q = warp & 3;
-        int it = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int half = (warp - 4) >> 2;
+        uint32_t chain = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             int tm, tn;
             tile_coords(t, tm, tn);
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            ptx::mbar_wait(tfull_bar(as), aphase);
-            ptx::tc_fence_after();
+            float acc[COLS];
+#pragma unroll
+            for (int i = 0; i < COLS; ++i) acc[i] = 0.f;
+            for (int kb0 = 0; kb0 < num_kb; kb0 += CHAIN, ++chain) {
+                const uint32_t as = chain & 1, aphase = (chain >> 1) & 1;
+                ptx::mbar_wait(tfull_bar(as), aphase);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem_base + as * BN + half * COLS + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+                for (int c = 0; c < COLS / 32; ++c) {
+                    float v[32];
+                    ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c * 32 + j] = __fadd_rn(acc[c * 32 + j], v[j]);  // round-to-nearest fold
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+            }
+            // tile finished: registers -> C (each thread owns one row, COLS consecutive columns)
             const int row = tm * BM + q * 32 + lane;
-            const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                float v[32];
-                ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
-                ptx::tmem_ld_wait();
-                const int col = tn * BN + c * 32;
-                if (row < p.M) {
-                    if (p.peers.world == 0) {
-                        float* dst = p.C + (size_t)row * p.ldc + col;
+            const int col0 = tn * BN + half * COLS;
+            if (row < p.M) {
+                if (p.peers.world == 0) {
+                    float* dst = p.C + (size_t)row * p.ldc + col0;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (col + 4 * j < p.N)
-                                *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    } else {
+                    for (int j = 0; j < COLS / 4; ++j)
+                        if (col0 + 4 * j < p.N)
+                            *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                } else {
 #pragma unroll 1
-                        for (int pr = 0; pr < p.peers.world; ++pr) {
-                            float* dst = p.peers.c[pr] + (size_t)row * p.peers.ldc + p.peers.col0 + col;
+                    for (int pr = 0; pr < p.peers.world; ++pr) {
+                        float* dst = p.peers.c[pr] + (size_t)row * p.peers.ldc + p.peers.col0 + col0;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                if (col + 4 * j < p.N)
-                                    *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        }
+                        for (int j = 0; j < COLS / 4; ++j)
+                            if (col0 + 4 * j < p.N)
+                                *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
                     }
                 }
             }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
         }
     }
 

@@ -1,0 +1,139 @@
+"""N-sharded SGEMM / GEMV across the GPUs of one box (new work defined by north_star).
+
+One process per GPU.  A (M x K) is replicated, B (K x N) and C are cut into `world` column panels; rank r
+computes C[:, r*N/g : (r+1)*N/g] and every rank ends the step holding the full row-major C.  Two ways
+to get the panels everywhere:
+
+  fused  the SGEMM epilogue stores each finished tile straight into the final (row, column) position of
+         the full C on EVERY rank through CUDA-IPC peer mappings over NVLink, tile by tile while later
+         tiles are still computing -- no collective, no interleave pass;
+  nccl   panel GEMM into a contiguous [M][N/g] buffer, one NCCL all-gather (layout [g][M][N/g]), then
+         b200mm_unshard_columns interleaves the panels into row-major C.  This is the baseline.
+
+torch.distributed is used for rendezvous, handle exchange, the NCCL all-gather and barriers only.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass(frozen=True)
+class ShardPlan:
+    """Column partition of an N-wide matrix over `world` ranks (contiguous, equal panels)."""
+    N: int
+    world: int
+    rank: int
+
+    def __post_init__(self):
+        if self.world <= 0 or not (0 <= self.rank < self.world):
+            raise ValueError(f"bad rank/world {self.rank}/{self.world}")
+        if self.N % (4 * self.world) != 0:
+            raise ValueError(f"N={self.N} must be a multiple of 4*world={4 * self.world} (float4 panels)")
+
+    @property
+    def cols(self) -> int:
+        return self.N // self.world
+
+    @property
+    def col0(self) -> int:
+        return self.rank * self.cols
+
+    def panel_of(self, r: int):
+        return (r * self.cols, (r + 1) * self.cols)
+
+    def gathered_to_row_major(self, gathered: np.ndarray, M: int) -> np.ndarray:
+        """Host restatement of b200mm_unshard_columns: [world][M][cols] -> [M][N] (tests / documentation)."""
+        g = np.asarray(gathered).reshape(self.world, M, self.cols)
+        return np.ascontiguousarray(np.transpose(g, (1, 0, 2)).reshape(M, self.N))
+
+
+class ShardedSgemm:
+    """One 16384^3-style job on this rank.  Requires torch.distributed (NCCL) to be initialised."""
+
+    def __init__(self, ctx, M: int, N: int, K: int, plan: ShardPlan, mode: str = "fused", kernel_id=None, seed: int = 100, tc_bn: int = 256):
+        import torch
+        import torch.distributed as dist
+        import wgpu_mm_b200 as w
+
+        self.torch, self.dist, self.w = torch, dist, w
+        self.ctx, self.M, self.N, self.K, self.plan, self.mode = ctx, M, N, K, plan, mode
+        self.stream = torch.cuda.Stream()
+        torch.cuda.set_stream(self.stream)
+        ctx.set_stream(self.stream.cuda_stream)  # our kernels and NCCL's waits share one stream
+        Np = plan.cols
+        kid = kernel_id if kernel_id is not None else w.KernelId.SGEMM_TC3X
+        # operands: A replicated (same stream positions on every rank), B panel = columns [col0, col0+Np) of the full B
+        self.A = ctx.buffer(M * K * 4)
+        self.A.fill_weights(seed + 1, M * K)
+        self.Bp = ctx.buffer(K * Np * 4)
+        self.Bp.fill_weights_2d(seed + 2, K, Np, N, plan.col0)
+        self.C = ctx.buffer(M * N * 4)  # full result, cudaMalloc'd by the library so it can be IPC-exported
+        self.peers = []
+        self._flag = torch.zeros(1, device="cuda")
+        if mode == "fused":
+            self.kern = ctx.kernel(kid, M, Np, K, w.KernelParams(flags=int(w.Flags.PEER_STORE), tune=(tc_bn, 0, 0, 0)))
+            handles = [None] * plan.world
+            dist.all_gather_object(handles, self.C.ipc_export())
+            ptrs = []
+            for r in range(plan.world):
+                if r == plan.rank:
+                    ptrs.append(self.C.ptr)
+                else:
+                    pb = ctx.ipc_import(handles[r], M * N * 4)
+                    self.peers.append(pb)
+                    ptrs.append(pb.ptr)
+            self.kern.set_peers(plan.rank, plan.world, ptrs, N, plan.col0)
+            self.Cp_t = None
+        elif mode == "nccl":
+            self.kern = ctx.kernel(kid, M, Np, K, w.KernelParams(tune=(tc_bn, 0, 0, 0)))
+            self.Cp_t = torch.empty(M * Np, dtype=torch.float32, device="cuda")
+            self.G_t = torch.empty(plan.world * M * Np, dtype=torch.float32, device="cuda")
+            self.Cp = ctx.wrap(self.Cp_t.data_ptr(), M * Np * 4)
+        else:
+            raise ValueError(mode)
+        self.kern.profile(True)
+        ctx.sync()
+        dist.barrier()
+
+    def step(self):
+        """One full C = A*B on all ranks: every rank holds the complete row-major C when its stream drains."""
+        if self.mode == "fused":
+            self.ctx.launch(self.kern, self.A, self.Bp, self.C)
+            # tiny all-reduce on the same stream: step i+1 cannot start before every rank's stores of step i were issued
+            self.dist.all_reduce(self._flag)
+        else:
+            self.ctx.launch(self.kern, self.A, self.Bp, self.Cp)
+            self.dist.all_gather_into_tensor(self.G_t, self.Cp_t)
+            self.ctx.unshard_columns(self.G_t.data_ptr(), self.C.ptr, self.M, self.N, self.plan.world)
+
+    def barrier(self):
+        self.ctx.sync()
+        self.torch.cuda.synchronize()
+        self.dist.barrier()
+
+    def kernel_times(self):
+        return self.kern.profile_read(256)
+
+    def checksum(self, rows=(0, 1, 4095)):
+        """Sum of a few rows of the local copy of C (consistency across ranks is checked by the caller)."""
+        out = np.empty(self.N, dtype=np.float32)
+        acc = 0.0
+        for r in rows:
+            if r < self.M:
+                self.C.read_into(out, offset=r * self.N * 4)
+                acc += float(out.astype(np.float64).sum())
+        return acc
+
+    def e2e_info(self, value):
+        return getattr(self, "_e2e", {"value": None, "unit": "TFLOP/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                                      "note": "not measured in this run"})
+
+    def close(self):
+        self.barrier()
+        for b in self.peers:
+            b.free()
+        self.kern.free()
+        for b in (self.A, self.Bp, self.C):
+            b.free()
