@@ -202,7 +202,7 @@ def run_single(args):
     flop = 2.0 * M * N * K
 
     # ---------------- headline: tcgen05 3xTF32 SGEMM 4096^3 ----------------
-    tune = (args.tc_bn, 0, 0, 0)
+    tune = (args.tc_bn, 0, args.tc_bk, 0)
     kern = ctx.kernel(w.KernelId.SGEMM_TC3X, M, N, K, w.KernelParams(tune=tune))
     sets = make_sets(ctx, M, N, K, 3, 100)
     sampler = ClockSampler(0); sampler.start(); time.sleep(0.3)
@@ -380,6 +380,7 @@ def main():
     ap.add_argument("--mode", default="fused", choices=["fused", "nccl"], help="multi-GPU gather: peer stores from the epilogue, or NCCL all-gather")
     ap.add_argument("--size", type=int, default=16384, help="multi-GPU problem size (M=N=K)")
     ap.add_argument("--tc-bn", type=int, default=256, choices=[128, 256])
+    ap.add_argument("--tc-bk", type=int, default=0, choices=[0, 16, 32], help="k-block of the tcgen05 kernel (0 = library default)")
     ap.add_argument("--gemv-variant", type=int, default=0)
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

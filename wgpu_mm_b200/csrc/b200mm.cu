@@ -57,7 +57,12 @@ struct b200mm_kernel {
     // tc3x
     float *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
     CUtensorMap tmAh{}, tmAl{}, tmBh{}, tmBl{};
-    int tc_bn = 256;
+    int tc_bn = 256, tc_bk = 32;
+    float4* tc_partial = nullptr;
+    unsigned int* tc_flags = nullptr;
+    unsigned int tc_epoch = 0;
+    int tc_cpt = 1, tc_full_waves = 0;
+    long long tc_sk_units = 0;
     // gemv
     int splits = 1, rows_per_split = 0, panels = 0, gemv_variant = 0;
     float* partial = nullptr;
@@ -313,15 +318,17 @@ static PFN_encodeTiled get_encode_tiled() {
 }
 
 // A-like operand: row-major rows x cols f32, box = box_rows x 32 floats (128 B, SWIZZLE_128B), K-major.
-static int make_tmap_kmajor(b200mm_ctx* ctx, CUtensorMap* tm, const float* base, size_t rows, size_t cols, int box_rows) {
+static int make_tmap_kmajor(b200mm_ctx* ctx, CUtensorMap* tm, const float* base, size_t rows, size_t cols, int box_rows,
+                            int box_cols = 32) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return fail(ctx, B200MM_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {cols * sizeof(float)};
-    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, B200MM_ERR_CUDA, "cuTensorMapEncodeTiled(K-major) failed: %d", (int)r);
     return B200MM_OK;
@@ -368,9 +375,10 @@ extern "C" const char* b200mm_kernel_name(int id) {
     }
 }
 
-using Tc256 = Tc3xCfg<256, 2, false>;
-using Tc128 = Tc3xCfg<128, 3, false>;
-using Tc256x1 = Tc3xCfg<256, 4, true>;
+using Tc256 = Tc3xCfg<256, 2, false, 32>;     // 2 stages x 96 KB
+using Tc256k16 = Tc3xCfg<256, 4, false, 16>;  // 4 stages x 48 KB: same bytes in flight, finer refill granularity
+using Tc128 = Tc3xCfg<128, 3, false, 32>;
+using Tc256x1 = Tc3xCfg<256, 4, true, 32>;
 
 // gemv variants: 0: 8 warps, unroll 8, full-warp rows;  1: 8 warps, unroll 8, half-warp rows
 template <class T>
@@ -490,11 +498,26 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return fail(ctx, B200MM_ERR_INVALID, "shape too large");
     const bool one_pass = (k->prm.flags & B200MM_F_TC3X_1X) != 0;
     k->tc_bn = (k->prm.tune[0] == 128) ? 128 : 256;
+    k->tc_bk = (k->prm.tune[2] == 32) ? 32 : 16;  // default: BK = 16, 4 stages
     if (one_pass) k->tc_bn = 256;
+    if (one_pass || k->tc_bn == 128) k->tc_bk = 32;
     // workspace: hi / lo copies of both operands (+128 B so the 3-D view of a ragged N never leaves the allocation)
     const size_t a_bytes = M * K * sizeof(float), b_bytes = K * N * sizeof(float) + 128;
     const size_t a_al = ceil_div(a_bytes, 1024) * 1024, b_al = ceil_div(b_bytes, 1024) * 1024;
-    k->ws_bytes = one_pass ? (a_al + b_al) : 2 * (a_al + b_al);
+    // stream-K schedule (see Tc3xArgs): units = tiles x chains, one contiguous range per CTA
+    const int bk = k->tc_bk, chain = 256 / bk;
+    const size_t num_kb = ceil_div(K, bk);
+    k->tc_cpt = (int)ceil_div(num_kb, chain);
+    const size_t tiles_all = ceil_div(M, 128) * ceil_div(N, k->tc_bn);
+    const int sms = ctx->prop.multiProcessorCount;
+    // hybrid schedule: whole-tile waves while there are >= one tile per SM, stream-K over the remainder
+    const int grid_x = (int)std::min<long long>((long long)tiles_all * k->tc_cpt, sms);
+    k->tc_full_waves = (int)(tiles_all / grid_x);
+    if (k->prm.tune[1] == 1) k->tc_full_waves = 0;  // tune[1] = 1: pure stream-K (for experiments)
+    k->tc_sk_units = (long long)(tiles_all - (size_t)k->tc_full_waves * grid_x) * k->tc_cpt;
+    const size_t part_bytes = (size_t)grid_x * 128 * k->tc_bn * sizeof(float);
+    const size_t flag_bytes = ceil_div((size_t)grid_x * sizeof(unsigned int), 1024) * 1024;
+    k->ws_bytes = (one_pass ? (a_al + b_al) : 2 * (a_al + b_al)) + part_bytes + flag_bytes;
     CU_TRY(ctx, cudaMalloc(&k->ws, k->ws_bytes));
     char* w = (char*)k->ws;
     k->a_hi = (float*)w;
@@ -507,23 +530,28 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
         k->b_lo = (float*)w;
         w += b_al;
     }
+    k->tc_partial = (float4*)w;
+    w += part_bytes;
+    k->tc_flags = (unsigned int*)w;
     CU_TRY(ctx, cudaMemsetAsync(k->ws, 0, k->ws_bytes, ctx->stream));
     int rc;
-    if ((rc = make_tmap_kmajor(ctx, &k->tmAh, k->a_hi, M, K, 128))) return rc;
-    if ((rc = make_tmap_mnmajor(ctx, &k->tmBh, k->b_hi, K, N, 32, k->tc_bn))) return rc;
+    if ((rc = make_tmap_kmajor(ctx, &k->tmAh, k->a_hi, M, K, 128, bk))) return rc;
+    if ((rc = make_tmap_mnmajor(ctx, &k->tmBh, k->b_hi, K, N, bk, k->tc_bn))) return rc;
     if (!one_pass) {
-        if ((rc = make_tmap_kmajor(ctx, &k->tmAl, k->a_lo, M, K, 128))) return rc;
-        if ((rc = make_tmap_mnmajor(ctx, &k->tmBl, k->b_lo, K, N, 32, k->tc_bn))) return rc;
+        if ((rc = make_tmap_kmajor(ctx, &k->tmAl, k->a_lo, M, K, 128, bk))) return rc;
+        if ((rc = make_tmap_mnmajor(ctx, &k->tmBl, k->b_lo, K, N, bk, k->tc_bn))) return rc;
     } else {
         k->tmAl = k->tmAh;
         k->tmBl = k->tmBh;
     }
-    const int tiles = (int)(ceil_div(M, 128) * ceil_div(N, k->tc_bn));
-    k->grid = dim3(std::min(tiles, ctx->prop.multiProcessorCount), 1, 1);
+    k->grid = dim3(grid_x, 1, 1);
     k->block = dim3(Tc256::THREADS, 1, 1);
     if (one_pass) {
         k->smem = Tc256x1::SMEM_BYTES;
         CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc256x1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
+    } else if (k->tc_bn == 256 && k->tc_bk == 16) {
+        k->smem = Tc256k16::SMEM_BYTES;
+        CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc256k16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
     } else if (k->tc_bn == 256) {
         k->smem = Tc256::SMEM_BYTES;
         CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
@@ -698,6 +726,13 @@ static void launch_tc3x(b200mm_kernel* k, cudaStream_t s, float* C) {
     a.ldc = (int)k->N;
     a.tiles_m = (int)ceil_div(k->M, Cfg::BM);
     a.tiles_n = (int)ceil_div(k->N, Cfg::BN);
+    a.chains_per_tile = k->tc_cpt;
+    a.full_waves = k->tc_full_waves;
+    a.sk_units = k->tc_sk_units;
+    a.partial = k->tc_partial;
+    a.flags = k->tc_flags;
+    a.epoch = ++k->tc_epoch;
+    static_assert(Cfg::CHAIN * Cfg::BK == 256, "setup_tc3x assumes chains of 256 k");
     a.peers = k->peers;
     sgemm_tc3x_kernel<Cfg><<<k->grid, k->block, k->smem, s>>>(k->tmAh, k->tmAl, k->tmBh, k->tmBl, a);
 }
@@ -767,7 +802,9 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
                 split_tf32_kernel<<<sms * 8, 256, 0, s>>>((const float4*)B, (float4*)k->b_hi, (float4*)k->b_lo, b4);
                 ctx->launches += 2;
                 prof_begin();
-                if (k->tc_bn == 256)
+                if (k->tc_bn == 256 && k->tc_bk == 16)
+                    launch_tc3x<Tc256k16>(k, s, Cf);
+                else if (k->tc_bn == 256)
                     launch_tc3x<Tc256>(k, s, Cf);
                 else
                     launch_tc3x<Tc128>(k, s, Cf);

@@ -150,6 +150,16 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, float (&v)[32
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, float (&v)[16]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 }  // namespace ptx
@@ -163,7 +173,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   layout 1 = SWIZZLE_128B_BASE32B  32-byte chunks XOR (row % 4); 4-row atoms.  The ONLY layout the tensor core
 //                                    accepts for MN-major 32-bit (tf32) operands -- with layout 2 the MMA silently
 //                                    produces zeros (measured, tools/probe_tc.py).  TMA side: SWIZZLE_128B_ATOM_32B.
-constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32B = 1;
+//   layout 4 = SWIZZLE_64B           16-byte chunks XOR ((row / 2) % 4); 8-row x 64-byte atoms (K-major A tiles when BK = 16).
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32B = 1, kLayoutSw64 = 4;
 __host__ __device__ constexpr uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(layout & 7u) << 61);
@@ -179,22 +190,68 @@ struct Tc3xArgs {
     float* C;
     int M, N, K, ldc;
     int tiles_m, tiles_n;
+    // Hybrid schedule.  Phase 1 (data-parallel): full_waves rounds of whole tiles, tile = wave * gridDim.x + blockIdx.x,
+    // so the CTAs of a wave walk K in lock-step and share operand panels in L2.  Phase 2 (stream-K) covers the
+    // remaining tiles (num_tiles % gridDim.x, or all of them when there are fewer tiles than CTAs): their
+    // (tile, chain) units, in tile-major order, are cut into gridDim.x equal contiguous ranges.  A CTA whose range
+    // starts inside a tile ("contributor") parks its partial accumulators in partial[blockIdx.x] and raises
+    // flags[blockIdx.x] = epoch; the CTA that holds chain 0 of the tile ("owner") adds the contributions of the
+    // following CTAs in CTA order (deterministic) and stores C.  4096^3: 512 tiles on 148 SMs = 3 waves + 68 tiles
+    // split 148 ways instead of a 4th wave that leaves 80 SMs idle.
+    int chains_per_tile;
+    int full_waves;
+    long long sk_units;     // stream-K units = remaining tiles x chains_per_tile
+    float4* partial;        // [gridDim.x][BN/8][256] float4
+    unsigned int* flags;    // [gridDim.x]
+    unsigned int epoch;     // bumped by the host on every launch, so flags never need clearing
     PeerStore peers;
+};
+
+struct SegIter {  // identical iteration in the producer, issuer and epilogue roles
+    long long u, u1;
+    int cpt, wave, full_waves, sk_tile0;
+    __device__ SegIter(const Tc3xArgs& p) : cpt(p.chains_per_tile), wave(0), full_waves(p.full_waves) {
+        sk_tile0 = p.full_waves * (int)gridDim.x;
+        u = (long long)blockIdx.x * p.sk_units / gridDim.x;
+        u1 = (long long)(blockIdx.x + 1) * p.sk_units / gridDim.x;
+    }
+    // c0 != 0 => contributor segment; c0 == 0 && c1 != cpt => owner of a split tile; sk_tile = tile index inside phase 2
+    __device__ bool next(int& tile, int& c0, int& c1, int& sk_tile) {
+        if (wave < full_waves) {
+            tile = wave * (int)gridDim.x + (int)blockIdx.x;
+            c0 = 0;
+            c1 = cpt;
+            sk_tile = -1;
+            ++wave;
+            return true;
+        }
+        if (u >= u1) return false;
+        sk_tile = (int)(u / cpt);
+        tile = sk_tile0 + sk_tile;
+        c0 = (int)(u % cpt);
+        const long long n = min((long long)(cpt - c0), u1 - u);
+        c1 = c0 + (int)n;
+        u += n;
+        return true;
+    }
 };
 
 // CHAIN: number of k-blocks accumulated inside TMEM before the partial sum is folded into fp32 registers.
 // Measured on B200 (tools/debug_tc3x.py): the tensor core adds into its fp32 accumulator with truncation, so a
 // single chain over K = 4096 (1536 accumulate steps) is biased by ~1e-4 -- 10x worse than a sequential fp32 loop.
 // Chains of 8 k-blocks (256 k, 96 steps) folded with round-to-nearest FADDs bring the error back to the fp32 level.
-template <int BN_, int STAGES_, bool ONE_PASS_, int CHAIN_ = 8>
+template <int BN_, int STAGES_, bool ONE_PASS_, int BK_ = 32, int CHAIN_K_ = 256>
 struct Tc3xCfg {
-    static constexpr int BM = 128, BN = BN_, BK = 32, STAGES = STAGES_, CHAIN = CHAIN_;
+    static constexpr int BM = 128, BN = BN_, BK = BK_, STAGES = STAGES_, CHAIN = CHAIN_K_ / BK_;
+    static_assert(BK == 32 || BK == 16, "A tile rows are 128 B (SWIZZLE_128B) or 64 B (SWIZZLE_64B)");
+    static constexpr uint32_t A_LAYOUT = BK == 32 ? kLayoutSw128 : kLayoutSw64;
+    static constexpr uint32_t A_SBO = 8 * BK * 4;               // 8 rows of BK floats
     static constexpr bool ONE_PASS = ONE_PASS_;
     static constexpr int EPI_WARPS = 8;                        // two warpgroups, each owns half of the BN columns
     static constexpr int THREADS = 128 + EPI_WARPS * 32;       // warps 0-3: TMA / MMA / TMEM alloc / idle
     static constexpr int COLS_PER_WG = BN / 2;
-    static constexpr uint32_t A_BYTES = BM * BK * 4;           // 16 KiB, 128 rows x 128 B, SWIZZLE_128B, K-major
-    static constexpr uint32_t B_BYTES = BK * BN * 4;           // BN/32 atoms x (32 k-rows x 128 B), SWIZZLE_128B_BASE32B, MN-major
+    static constexpr uint32_t A_BYTES = BM * BK * 4;           // 128 rows x BK floats, K-major
+    static constexpr uint32_t B_BYTES = BK * BN * 4;           // BN/32 atoms x (BK k-rows x 128 B), SWIZZLE_128B_BASE32B, MN-major
     static constexpr uint32_t STAGE_BYTES = (ONE_PASS ? 1 : 2) * (A_BYTES + B_BYTES);
     static constexpr uint32_t TMEM_COLS = 2 * BN;              // two chain accumulators (ping-pong)
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -225,7 +282,6 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     auto sB_lo = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * A_BYTES + B_BYTES; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = p.tiles_m * p.tiles_n;
     const int num_kb = (p.K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
@@ -269,10 +325,13 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             if (lane == 0) {
                 int stage = 0;
                 uint32_t phase = 0;
-                for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                SegIter it(p);
+                int t, c0, c1, skt;
+                while (it.next(t, c0, c1, skt)) {
                     int tm, tn;
                     tile_coords(t, tm, tn);
-                    for (int kb = 0; kb < num_kb; ++kb) {
+                    const int kb_end = min(c1 * CHAIN, num_kb);
+                    for (int kb = c0 * CHAIN; kb < kb_end; ++kb) {
                         ptx::mbar_wait(empty_bar(stage), phase ^ 1);
                         ptx::mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
                         ptx::tma_load_2d(sA_hi(stage), &tmAh, full_bar(stage), kb * BK, tm * BM);
@@ -295,8 +354,10 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
                 int stage = 0;
                 uint32_t phase = 0;
                 uint32_t chain = 0;  // running chain index: TMEM buffer = chain & 1
-                for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                    for (int kb0 = 0; kb0 < num_kb; kb0 += CHAIN, ++chain) {
+                SegIter it(p);
+                int t, c0, c1, skt;
+                while (it.next(t, c0, c1, skt)) {
+                    for (int kb0 = c0 * CHAIN; kb0 < min(c1 * CHAIN, num_kb); kb0 += CHAIN, ++chain) {
                         const uint32_t as = chain & 1, aphase = (chain >> 1) & 1;
                         ptx::mbar_wait(tempty_bar(as), aphase ^ 1);  // epilogue has drained this accumulator
                         ptx::tc_fence_after();
@@ -308,13 +369,13 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
 #pragma unroll
                             for (int j = 0; j < BK / 8; ++j) {
                                 // A (K-major, SWIZZLE_128B): 8 tf32 = 32 B along the swizzled row; SBO = 8 rows x 128 B
-                                const uint64_t a_hi = make_smem_desc(sA_hi(stage) + j * 32, 16, 1024, kLayoutSw128);
+                                const uint64_t a_hi = make_smem_desc(sA_hi(stage) + j * 32, 16, Cfg::A_SBO, Cfg::A_LAYOUT);
                                 // B (MN-major, SWIZZLE_128B_BASE32B): 8 k-rows = two 4-row atoms (SBO = 512 B) per MMA;
                                 // LBO = stride between 32-column atoms = BK rows x 128 B
                                 const uint64_t b_hi = make_smem_desc(sB_hi(stage) + j * 1024, BK * 128, 512, kLayoutSw128Base32B);
                                 const uint32_t acc0 = (kb > kb0 || j > 0) ? 1u : 0u;  // first MMA of a chain overwrites
                                 if (!ONE_PASS) {
-                                    const uint64_t a_lo = make_smem_desc(sA_lo(stage) + j * 32, 16, 1024, kLayoutSw128);
+                                    const uint64_t a_lo = make_smem_desc(sA_lo(stage) + j * 32, 16, Cfg::A_SBO, Cfg::A_LAYOUT);
                                     const uint64_t b_lo = make_smem_desc(sB_lo(stage) + j * 1024, BK * 128, 512, kLayoutSw128Base32B);
                                     ptx::mma_tf32_ss(d_tmem, a_lo, b_hi, idesc, acc0);  // small terms first
                                     ptx::mma_tf32_ss(d_tmem, a_hi, b_lo, idesc, 1u);
@@ -341,28 +402,61 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
         uint32_t chain = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int etid = threadIdx.x - 128;  // 0..255 inside the epilogue group
+        SegIter it(p);
+        int t, c0, c1, skt;
+        while (it.next(t, c0, c1, skt)) {
             int tm, tn;
             tile_coords(t, tm, tn);
             float acc[COLS];
 #pragma unroll
             for (int i = 0; i < COLS; ++i) acc[i] = 0.f;
-            for (int kb0 = 0; kb0 < num_kb; kb0 += CHAIN, ++chain) {
+            for (int kb0 = c0 * CHAIN; kb0 < min(c1 * CHAIN, num_kb); kb0 += CHAIN, ++chain) {
                 const uint32_t as = chain & 1, aphase = (chain >> 1) & 1;
                 ptx::mbar_wait(tfull_bar(as), aphase);
                 ptx::tc_fence_after();
                 const uint32_t taddr = tmem_base + as * BN + half * COLS + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-                for (int c = 0; c < COLS / 32; ++c) {
-                    float v[32];
-                    ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+                for (int c = 0; c < COLS / 16; ++c) {
+                    float v[16];
+                    ptx::tmem_ld_32x32b_x16(taddr + c * 16, v);
                     ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[c * 32 + j] = __fadd_rn(acc[c * 32 + j], v[j]);  // round-to-nearest fold
+                    for (int j = 0; j < 16; ++j) acc[c * 16 + j] = __fadd_rn(acc[c * 16 + j], v[j]);  // round-to-nearest fold
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+            }
+            if (c0 != 0) {
+                // contributor: this range starts inside the tile -> park the partial sums for the owner
+                float4* slot = p.partial + (size_t)blockIdx.x * (COLS / 4) * 256;
+#pragma unroll
+                for (int j = 0; j < COLS / 4; ++j) slot[j * 256 + etid] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                __threadfence();
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // all 8 epilogue warps have published their part
+                if (etid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.flags + blockIdx.x), "r"(p.epoch) : "memory");
+                continue;
+            }
+            if (c1 != p.chains_per_tile) {
+                // owner of a tile that continues in the following CTAs: add their parts in CTA order
+                const long long tile_end = (long long)(skt + 1) * p.chains_per_tile;
+                for (int j = blockIdx.x + 1; j < (int)gridDim.x; ++j) {
+                    if ((long long)j * p.sk_units / gridDim.x >= tile_end) break;
+                    unsigned int seen;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.flags + j) : "memory");
+                    } while (seen != p.epoch);
+                    const float4* slot = p.partial + (size_t)j * (COLS / 4) * 256;
+#pragma unroll
+                    for (int jj = 0; jj < COLS / 4; ++jj) {
+                        const float4 w = __ldcg(slot + jj * 256 + etid);
+                        acc[4 * jj] = __fadd_rn(acc[4 * jj], w.x);
+                        acc[4 * jj + 1] = __fadd_rn(acc[4 * jj + 1], w.y);
+                        acc[4 * jj + 2] = __fadd_rn(acc[4 * jj + 2], w.z);
+                        acc[4 * jj + 3] = __fadd_rn(acc[4 * jj + 3], w.w);
+                    }
+                }
             }
             // tile finished: registers -> C (each thread owns one row, COLS consecutive columns)
             const int row = tm * BM + q * 32 + lane;
