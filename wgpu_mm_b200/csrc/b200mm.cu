@@ -58,6 +58,8 @@ struct b200mm_kernel {
     float *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
     CUtensorMap tmAh{}, tmAl{}, tmBh{}, tmBl{};
     int tc_bn = 256, tc_bk = 32;
+    const void *tc_a_src = nullptr, *tc_b_src = nullptr;  // operands the hi tensor maps currently point at
+    bool tc_b_copy = false;                               // ragged N: B is staged into a padded copy first
     float4* tc_partial = nullptr;
     unsigned int* tc_flags = nullptr;
     unsigned int tc_epoch = 0;
@@ -501,9 +503,11 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     k->tc_bk = (k->prm.tune[2] == 32) ? 32 : 16;  // default: BK = 16, 4 stages
     if (one_pass) k->tc_bn = 256;
     if (one_pass || k->tc_bn == 128) k->tc_bk = 32;
-    // workspace: hi / lo copies of both operands (+128 B so the 3-D view of a ragged N never leaves the allocation)
+    // workspace: lo parts of both operands (the raw operands are consumed as hi); for N % 32 != 0 also a padded
+    // copy of B, because the 3-D view (n%32, k, n/32) of a ragged N reads up to 124 B past the last row
     const size_t a_bytes = M * K * sizeof(float), b_bytes = K * N * sizeof(float) + 128;
     const size_t a_al = ceil_div(a_bytes, 1024) * 1024, b_al = ceil_div(b_bytes, 1024) * 1024;
+    k->tc_b_copy = (N % 32) != 0;
     // stream-K schedule (see Tc3xArgs): units = tiles x chains, one contiguous range per CTA
     const int bk = k->tc_bk, chain = 256 / bk;
     const size_t num_kb = ceil_div(K, bk);
@@ -517,17 +521,17 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     k->tc_sk_units = (long long)(tiles_all - (size_t)k->tc_full_waves * grid_x) * k->tc_cpt;
     const size_t part_bytes = (size_t)grid_x * 128 * k->tc_bn * sizeof(float);
     const size_t flag_bytes = ceil_div((size_t)grid_x * sizeof(unsigned int), 1024) * 1024;
-    k->ws_bytes = (one_pass ? (a_al + b_al) : 2 * (a_al + b_al)) + part_bytes + flag_bytes;
+    k->ws_bytes = (one_pass ? 0 : (a_al + b_al)) + (k->tc_b_copy ? b_al : 0) + part_bytes + flag_bytes;
     CU_TRY(ctx, cudaMalloc(&k->ws, k->ws_bytes));
     char* w = (char*)k->ws;
-    k->a_hi = (float*)w;
-    w += a_al;
-    k->b_hi = (float*)w;
-    w += b_al;
     if (!one_pass) {
         k->a_lo = (float*)w;
         w += a_al;
         k->b_lo = (float*)w;
+        w += b_al;
+    }
+    if (k->tc_b_copy) {
+        k->b_hi = (float*)w;
         w += b_al;
     }
     k->tc_partial = (float4*)w;
@@ -535,15 +539,11 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     k->tc_flags = (unsigned int*)w;
     CU_TRY(ctx, cudaMemsetAsync(k->ws, 0, k->ws_bytes, ctx->stream));
     int rc;
-    if ((rc = make_tmap_kmajor(ctx, &k->tmAh, k->a_hi, M, K, 128, bk))) return rc;
-    if ((rc = make_tmap_mnmajor(ctx, &k->tmBh, k->b_hi, K, N, bk, k->tc_bn))) return rc;
     if (!one_pass) {
         if ((rc = make_tmap_kmajor(ctx, &k->tmAl, k->a_lo, M, K, 128, bk))) return rc;
         if ((rc = make_tmap_mnmajor(ctx, &k->tmBl, k->b_lo, K, N, bk, k->tc_bn))) return rc;
-    } else {
-        k->tmAl = k->tmAh;
-        k->tmBl = k->tmBh;
     }
+    // the hi maps point at the caller's A and B and are (re)encoded at launch time
     k->grid = dim3(grid_x, 1, 1);
     k->block = dim3(Tc256::THREADS, 1, 1);
     if (one_pass) {
@@ -791,16 +791,30 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
             const bool one_pass = (k->prm.flags & B200MM_F_TC3X_1X) != 0;
             const int sms = ctx->prop.multiProcessorCount;
             const size_t a4 = k->M * k->K / 4, b4 = k->K * k->N / 4;
-            if (one_pass) {
-                // single-pass TF32: operands go in as they are (the tensor core drops the low mantissa bits)
-                CU_TRY(ctx, cudaMemcpyAsync(k->a_hi, A, a4 * 16, cudaMemcpyDeviceToDevice, s));
+            if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return fail(ctx, B200MM_ERR_INVALID, "sgemm_tc3x needs 16-byte aligned A, B, C");
+            // hi operands = the caller's buffers (the tensor core truncates them to tf32); re-encode the maps when they move
+            const void* b_src = B;
+            if (k->tc_b_copy) {
                 CU_TRY(ctx, cudaMemcpyAsync(k->b_hi, B, b4 * 16, cudaMemcpyDeviceToDevice, s));
+                b_src = k->b_hi;
+            }
+            int rc;
+            if (k->tc_a_src != A) {
+                if ((rc = make_tmap_kmajor(ctx, &k->tmAh, (const float*)A, k->M, k->K, 128, k->tc_bk))) return rc;
+                k->tc_a_src = A;
+            }
+            if (k->tc_b_src != b_src) {
+                if ((rc = make_tmap_mnmajor(ctx, &k->tmBh, (const float*)b_src, k->K, k->N, k->tc_bk, k->tc_bn))) return rc;
+                k->tc_b_src = b_src;
+            }
+            if (one_pass) {
+                k->tmAl = k->tmAh;
+                k->tmBl = k->tmBh;
                 prof_begin();
                 launch_tc3x<Tc256x1>(k, s, Cf);
             } else {
-                split_tf32_kernel<<<sms * 8, 256, 0, s>>>((const float4*)A, (float4*)k->a_hi, (float4*)k->a_lo, a4);
-                split_tf32_kernel<<<sms * 8, 256, 0, s>>>((const float4*)B, (float4*)k->b_hi, (float4*)k->b_lo, b4);
-                ctx->launches += 2;
+                split_lo_kernel<<<sms * 8, 256, 0, s>>>((const float4*)A, (float4*)k->a_lo, a4, (const float4*)B, (float4*)k->b_lo, b4);
+                ctx->launches += 1;
                 prof_begin();
                 if (k->tc_bn == 256 && k->tc_bk == 16)
                     launch_tc3x<Tc256k16>(k, s, Cf);

@@ -8,10 +8,12 @@
 // (shaders/gemm/gemm_5.wgsl:15-86 and the orphan bram/gemm3 kernels) for C = A*B with
 // A (M x K), B (K x N), C (M x N) row-major f32 (src/harness.rs:17-28 fixes the layout).
 //
+//     x = hi + lo,  hi = trunc_tf32(x) -- applied by the tensor core itself to the raw operand --, lo = tf32(x - hi)
+//
 // Two kernels per GEMM:
-//   1. split_tf32_kernel   elementwise pass, HBM-bound: reads A and B once, writes A_hi, A_lo, B_hi, B_lo
-//                          (kind::tf32 ignores the low 13 mantissa bits of its 32-bit operands, so hi and lo
-//                          must be materialised as exactly-representable tf32 values);
+//   1. split_lo_kernel     elementwise pass, HBM-bound: reads A and B once, writes A_lo and B_lo
+//                          (kind::tf32 ignores the low 13 mantissa bits of its 32-bit operands: the raw operand
+//                          is consumed as hi, lo must be materialised);
 //   2. sgemm_tc3x_kernel   persistent, warp-specialised:
 //        warp 0    TMA producer: per k-block loads A_hi/A_lo (128 x 32, K-major, SWIZZLE_128B) and
 //                  B_hi/B_lo (32 x BN, N-major: B is K x N row-major, so it is consumed as an MN-major
@@ -58,6 +60,26 @@ __global__ void split_tf32_kernel(const float4* __restrict__ x, float4* __restri
         h.w = to_tf32_rna(v.w); l.w = to_tf32_rna(v.w - h.w);
         hi[i] = h;
         lo[i] = l;
+    }
+}
+
+// Production split: the tensor core TRUNCATES the low 13 mantissa bits of a kind::tf32 operand (measured,
+// tools/probe_tc.py), so the raw fp32 operand already acts as hi = trunc(x) and only lo = tf32(x - trunc(x))
+// has to be materialised (x - trunc(x) is exact in fp32).  One launch covers A and B: reads 2 x 64 MB and
+// writes 2 x 64 MB at 4096^3 instead of 2 x 64 / 4 x 64 for the hi+lo version above.
+__global__ void split_lo_kernel(const float4* __restrict__ a, float4* __restrict__ a_lo, size_t a4,
+                                const float4* __restrict__ b, float4* __restrict__ b_lo, size_t b4) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    auto lo1 = [](float x) { return to_tf32_rna(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); };
+    for (; i < a4 + b4; i += stride) {
+        const bool is_a = i < a4;
+        const float4 v = __ldg(is_a ? a + i : b + (i - a4));
+        const float4 l = make_float4(lo1(v.x), lo1(v.y), lo1(v.z), lo1(v.w));
+        if (is_a)
+            a_lo[i] = l;
+        else
+            b_lo[i - a4] = l;
     }
 }
 
