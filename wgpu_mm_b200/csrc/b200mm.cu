@@ -399,6 +399,22 @@ static void gemv_pick(int variant, void (**fn)(const float*, const void*, float*
         *fn = gemv_stream_kernel<T, 8, 4, 32>;
         *warps = 8;
         *lpr = 32;
+    } else if (variant == 4) {
+        *fn = gemv_stream_kernel<T, 8, 4, 16>;
+        *warps = 8;
+        *lpr = 16;
+    } else if (variant == 5) {
+        *fn = gemv_stream_kernel<T, 4, 4, 32>;
+        *warps = 4;
+        *lpr = 32;
+    } else if (variant == 6) {
+        *fn = gemv_stream_kernel<T, 4, 8, 16>;
+        *warps = 4;
+        *lpr = 16;
+    } else if (variant == 7) {
+        *fn = gemv_stream_kernel<T, 4, 4, 16>;
+        *warps = 4;
+        *lpr = 16;
     } else {
         *fn = gemv_stream_kernel<T, 8, 8, 32>;
         *warps = 8;
@@ -569,7 +585,8 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     if (N % cols || K % 4)
         return fail(ctx, B200MM_ERR_INVALID, "%s needs N%%%d==0 and K%%4==0", b200mm_kernel_name(k->id), cols);
     if (N > INT32_MAX || K > INT32_MAX) return fail(ctx, B200MM_ERR_INVALID, "shape too large");
-    k->gemv_variant = (int)k->prm.tune[0];
+    // tune[0]: 0 = default for the weight type (measured on B200, tools/sweep_gemv.py), 100 = variant 0, else the variant id
+    k->gemv_variant = k->prm.tune[0] == 0 ? (quant ? 4 : 0) : (k->prm.tune[0] == 100 ? 0 : (int)k->prm.tune[0]);
     void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t);
     int warps, lpr;
     if (quant)
@@ -579,13 +596,20 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     const int panel = lpr * cols;
     const unsigned batch = k->prm.batch ? k->prm.batch : 1;
     k->panels = (int)ceil_div(N, panel);
-    // K-splits: aim at ~4 CTAs per SM in flight, at least 64 rows per split, at most 64 splits
+    // K-splits: fill exactly ONE wave.  A second, partial wave runs at a fraction of the bandwidth (few CTAs, few
+    // loads in flight) and was measured to cost 25 % at cfg3, so the split count is rounded DOWN to what is
+    // co-resident: SMs x occupancy of this instantiation (registers, x staging + reduction smem).
     int splits = (int)k->prm.tune[1];
     if (splits <= 0) {
-        const size_t target = (size_t)ctx->prop.multiProcessorCount * 4;
-        splits = (int)ceil_div(target, (size_t)k->panels * batch);
+        int occ = 1;
+        const size_t smem_guess = ((size_t)K / 4 + (size_t)warps * panel) * sizeof(float);
+        CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, warps * 32, smem_guess));
+        occ = std::max(1, std::min(occ, 2048 / (warps * 32)));
+        const size_t slots = (size_t)ctx->prop.multiProcessorCount * occ;
+        splits = (int)(slots / ((size_t)k->panels * batch));
         splits = std::max(1, std::min(splits, 64));
-        splits = (int)std::min<size_t>(splits, std::max<size_t>(1, K / 64));
+        splits = (int)std::min<size_t>(splits, std::max<size_t>(1, K / 32));
     }
     const int rstep = warps * (32 / lpr);
     size_t rps = ceil_div(K, (size_t)splits);
