@@ -276,7 +276,10 @@ struct Tc3xCfg {
     static constexpr uint32_t B_BYTES = BK * BN * 4;           // BN/32 atoms x (BK k-rows x 128 B), SWIZZLE_128B_BASE32B, MN-major
     static constexpr uint32_t STAGE_BYTES = (ONE_PASS ? 1 : 2) * (A_BYTES + B_BYTES);
     static constexpr uint32_t TMEM_COLS = 2 * BN;              // two chain accumulators (ping-pong)
-    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr uint32_t EPI_STAGE_LD = 32;                                   // floats per staged row; 16 B chunks XOR-swizzled by row
+    static constexpr uint32_t EPI_STAGE_BYTES = EPI_WARPS * 32 * EPI_STAGE_LD * 4;  // one 32 x 32 chunk per epilogue warp
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM cols: power of 2");
     static_assert(COLS_PER_WG % 32 == 0, "epilogue reads 32 columns per tcgen05.ld");
 };
@@ -480,24 +483,38 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
                     }
                 }
             }
-            // tile finished: registers -> C (each thread owns one row, COLS consecutive columns)
-            const int row = tm * BM + q * 32 + lane;
+            // tile finished: registers -> C.  Each thread owns one row x COLS columns; a direct store would write 16-byte
+            // pieces of 32 different rows per instruction.  Instead every warp transposes 32 x 32 chunks through its own
+            // 4 KB of shared memory (XOR-swizzled, conflict-free) so that each st.global.v4 covers 4 rows x 128 contiguous bytes -- full 128 B lines for
+            // HBM and for NVLink when the tile also goes to the peers (fused all-gather).
+            float* stage = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw))) + (warp - 4) * 32 * Cfg::EPI_STAGE_LD;
+            const int row0 = tm * BM + q * 32;
             const int col0 = tn * BN + half * COLS;
-            if (row < p.M) {
-                if (p.peers.world == 0) {
-                    float* dst = p.C + (size_t)row * p.ldc + col0;
+            const int ndst = p.peers.world == 0 ? 1 : p.peers.world;
+#pragma unroll  // must stay unrolled: acc[] is indexed with c and has to live in registers
+            for (int c = 0; c < COLS / 32; ++c) {
+                __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < COLS / 4; ++j)
-                        if (col0 + 4 * j < p.N)
-                            *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-                } else {
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(stage + lane * Cfg::EPI_STAGE_LD + 4 * (j ^ (lane & 7))) =
+                        make_float4(acc[c * 32 + 4 * j], acc[c * 32 + 4 * j + 1], acc[c * 32 + 4 * j + 2], acc[c * 32 + 4 * j + 3]);
+                __syncwarp();
+                const int cc = col0 + c * 32 + (lane & 7) * 4;
+                float4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = 4 * i + (lane >> 3);
+                    v[i] = *reinterpret_cast<const float4*>(stage + rr * Cfg::EPI_STAGE_LD + 4 * ((lane & 7) ^ (rr & 7)));
+                }
 #pragma unroll 1
-                    for (int pr = 0; pr < p.peers.world; ++pr) {
-                        float* dst = p.peers.c[pr] + (size_t)row * p.peers.ldc + p.peers.col0 + col0;
+                for (int d = 0; d < ndst; ++d) {
+                    float* base = p.peers.world == 0 ? p.C : p.peers.c[d];
+                    const size_t ld = p.peers.world == 0 ? (size_t)p.ldc : p.peers.ldc;
+                    const size_t coff = p.peers.world == 0 ? 0 : p.peers.col0;
 #pragma unroll
-                        for (int j = 0; j < COLS / 4; ++j)
-                            if (col0 + 4 * j < p.N)
-                                *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = row0 + 4 * i + (lane >> 3);
+                        if (r < p.M && cc < p.N) *reinterpret_cast<float4*>(base + (size_t)r * ld + coff + cc) = v[i];
                     }
                 }
             }

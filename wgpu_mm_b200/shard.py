@@ -126,9 +126,39 @@ class ShardedSgemm:
                 acc += float(out.astype(np.float64).sum())
         return acc
 
-    def e2e_info(self, value):
-        return getattr(self, "_e2e", {"value": None, "unit": "TFLOP/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
-                                      "note": "not measured in this run"})
+    def e2e(self, steps: int = 2):
+        """The same step through HOST buffers: per step H2D of this rank's inputs (A and its B panel) from pinned
+        memory, the sharded GEMM, and a D2H read of the full C.  Returns seconds per step (max over ranks)."""
+        import ctypes as C
+        import time
+        w, torch, dist = self.w, self.torch, self.dist
+        M, N, K, Np = self.M, self.N, self.K, self.plan.cols
+        hs = []
+        arrs = []
+        for nfloat in (M * K, K * Np, M * N):
+            h = C.c_void_p()
+            w._lib.check(w.lib().b200mm_host_alloc(nfloat * 4, C.byref(h)))
+            hs.append(h)
+            arrs.append(np.ctypeslib.as_array((C.c_float * nfloat).from_address(h.value)))
+        hA, hB, hC = arrs
+        self.A.read_into(hA)
+        self.Bp.read_into(hB)
+        times = []
+        for i in range(steps + 1):
+            self.barrier()
+            t0 = time.perf_counter()
+            self.A.write(hA)
+            self.Bp.write(hB)
+            self.step()
+            self.C.read_into(hC)  # blocking: ordered after the step's trailing collective on the same stream
+            dt = time.perf_counter() - t0
+            if i > 0:
+                times.append(dt)
+        t = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        for h in hs:
+            w.lib().b200mm_host_free(h)
+        return float(t.item()), (M * K + K * Np) * 4, M * N * 4
 
     def close(self):
         self.barrier()
