@@ -288,6 +288,17 @@ def run_single(args):
                                                          "algorithmic_bytes": qbytes, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['_source']})"}}
         kq.free(); free_sets(qsets)
 
+    if not args.no_extras:
+        # ---------------- SGEMM 16384^3 on ONE GPU: the strong-scaling baseline of the N-sharded runs ----------------
+        Mb = 16384
+        kb = ctx.kernel(w.KernelId.SGEMM_TC3X, Mb, Mb, Mb, w.KernelParams(tune=tune))
+        bsets = make_sets(ctx, Mb, Mb, Mb, 1, 700)
+        tot, per = time_kernel_steps(ctx, kb, bsets, 3, 2)
+        bflop = 2.0 * Mb * Mb * Mb
+        extras["sgemm_tc3x_16384_1gpu"] = {"tflops": bflop / (tot / 3 * 1e-3) / 1e12, "ms_per_step": tot / 3, "kernel_ms": float(np.mean(per)),
+                                           "note": "same kernel and schedule as the N-sharded runs; sustained clocks (power cap) apply"}
+        kb.free(); free_sets(bsets)
+
     # ---------------- CPU baseline (reported, not the target) ----------------
     cpu = None
     if not args.no_cpu:
@@ -354,6 +365,34 @@ def run_multi(args):
     dist.all_gather(cs_all, cs)
     consistent = all(float(c.item()) == float(cs_all[0].item()) for c in cs_all) and float(cs_all[0].item()) != 0.0
     e2e_s, h2d, d2h = job.e2e(2) if not args.no_e2e else (None, None, None)
+    job.close()
+    # ---- the GEMV configs, N-sharded over the same ranks (BASELINE configs[2], [3]) ----
+    extras = {}
+    if not args.no_extras:
+        for name, Kv, Nv, quant in (("gemv_f32_4096x16384", 4096, 16384, False), ("qgemv_sint8_4096x14336", 4096, 14336, True)):
+            if Nv % (16 * world):
+                continue
+            gplan = shard.ShardPlan(Nv, world, rank)
+            gj = shard.ShardedGemv(ctx, Kv, Nv, gplan, quant=quant, mode=args.mode)
+            for _ in range(10):
+                gj.step()
+            gj.barrier()
+            gj.kernel_times()
+            ctx.timer_begin()
+            for _ in range(50):
+                gj.step()
+            gms = ctx.timer_end()
+            gj.barrier()
+            kt = gj.kernel_times()
+            tt = torch.tensor([gms / 50, float(np.median(kt))], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            total_bytes = (Kv * Nv if quant else 4 * Kv * Nv) + 4 * Kv + 4 * Nv
+            step_us, kern_us = float(tt[0]) * 1e3, float(tt[1]) * 1e3
+            extras[name] = {"kernel_gbps_aggregate": total_bytes / (kern_us * 1e-6) / 1e9, "kernel_us_max_over_ranks": kern_us,
+                            "step_us_incl_gather": step_us, "step_gbps_aggregate": total_bytes / (step_us * 1e-6) / 1e9,
+                            "roofline": {"bound": "hbm", "achieved": total_bytes / (kern_us * 1e-6) / 1e9 / world, "peak": peaks["hbm_gbs"],
+                                         "unit": "GB/s per GPU", "frac": total_bytes / (kern_us * 1e-6) / 1e9 / world / peaks["hbm_gbs"]}}
+            gj.close()
     if rank == 0:
         clocks = sampler.stop(t0, t1)
         kern_ms = float(np.mean(per)) if per else ms / steps
@@ -372,10 +411,9 @@ def run_multi(args):
             "e2e": ({"value": flop / e2e_s / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                      "ms_per_step": e2e_s * 1e3, "api": "per rank: pinned host A + B panel -> device, sharded step, full C -> pinned host"}
                     if e2e_s else None),
-            "gpu_launches": int(launches), "clocks": clocks, "ranks_hold_identical_c": bool(consistent),
+            "gpu_launches": int(launches), "clocks": clocks, "ranks_hold_identical_c": bool(consistent), "extras": extras,
         }
         print(json.dumps(line), flush=True)
-    job.close()
     ctx.close()
     dist.destroy_process_group()
 

@@ -181,9 +181,10 @@ B200MM_API int b200mm_flush_l2(b200mm_ctx* ctx);
  * map it; the handles travel over the caller's control plane (torch.distributed / MPI). */
 B200MM_API int b200mm_ipc_export(b200mm_ctx* ctx, const b200mm_buffer* buf, void* handle64);
 B200MM_API int b200mm_ipc_import(b200mm_ctx* ctx, const void* handle64, size_t bytes, b200mm_buffer** out);
-/* Tell a SGEMM kernel object (created with B200MM_F_PEER_STORE) where the full row-major C (M x ldc)
- * lives on every rank and which column offset this rank's panel starts at.  The epilogue then
- * stores each finished tile to all `world` destinations over NVLink instead of a later all-gather. */
+/* Tell a SGEMM kernel object where the full row-major C (M x ldc) lives on every rank and which column
+ * offset this rank's panel starts at.  The epilogue then stores each finished tile to all `world`
+ * destinations over NVLink instead of a later all-gather.  For the GEMV kernels peer_c[] are the full
+ * y vectors (ldc is ignored) and col_offset the first output of this rank's slice. */
 B200MM_API int b200mm_kernel_set_peers(b200mm_kernel* kern, int rank, int world, void* const* peer_c, size_t ldc,
                                        size_t col_offset);
 /* After an NCCL all-gather of column panels (layout [world][M][N/world]) interleave them into

@@ -50,6 +50,32 @@ def main():
                   f"unwritten={unwritten} {'OK' if ok else 'FAIL'}", flush=True)
             failures += 0 if ok else 1
             job.close()
+    # ---- N-sharded GEMV (fp32 and sint8 in the quant.rs format) ----
+    Kv, Nv = 2048, 4096
+    x = oracle.generate_weight_data(301, 1, Kv)
+    Wf = oracle.generate_weight_data(302, Kv, Nv)
+    words, _ = oracle.sint8_quantize(Wf, Kv, Nv)
+    Wq = words.reshape(Kv, Nv // 4)
+    for mode in ("fused", "nccl"):
+        for quant in (False, True):
+            plan = shard.ShardPlan(Nv, world, rank)
+            if quant:
+                panel = np.ascontiguousarray(Wq[:, plan.col0 // 4:(plan.col0 + plan.cols) // 4])
+                want = oracle.qgemv_ref(x, words, 1, Nv, Kv, 2.0)
+                f64 = oracle.qgemv_f64(x, words, 1, Nv, Kv, 2.0)
+            else:
+                panel = np.ascontiguousarray(Wf[:, plan.col0:plan.col0 + plan.cols])
+                want = oracle.mm_ref(x, Wf)
+                f64 = oracle.mm_f64(x, Wf)
+            job = shard.ShardedGemv(ctx, Kv, Nv, plan, quant=quant, mode=mode, x_host=x, panel_host=panel)
+            job.step()
+            got = job.result().reshape(1, Nv)
+            e, m = oracle.err_vs_f64(got, f64)
+            mae = oracle.max_abs_err(got, want)
+            ok = (e / m <= 5e-6) and (mae <= 1e-3)
+            print(f"rank {rank}/{world} gemv mode={mode} quant={quant}: rel_f64={e / m:.3e} max_abs={mae:.3e} {'OK' if ok else 'FAIL'}", flush=True)
+            failures += 0 if ok else 1
+            job.close()
     t = torch.tensor([failures], device="cuda")
     dist.all_reduce(t)
     ctx.close()

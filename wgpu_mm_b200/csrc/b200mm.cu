@@ -385,7 +385,7 @@ using Tc256x1 = Tc3xCfg<256, 4, true, 32>;
 // gemv variants: 0: 8 warps, unroll 8, full-warp rows;  1: 8 warps, unroll 8, half-warp rows
 template <class T>
 static void gemv_pick(int variant, void (**fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float,
-                                               size_t, size_t, size_t),
+                                               size_t, size_t, size_t, PeerStore),
                       int* warps, int* lpr) {
     if (variant == 1) {
         *fn = gemv_stream_kernel<T, 8, 8, 16>;
@@ -587,7 +587,7 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     if (N > INT32_MAX || K > INT32_MAX) return fail(ctx, B200MM_ERR_INVALID, "shape too large");
     // tune[0]: 0 = default for the weight type (measured on B200, tools/sweep_gemv.py), 100 = variant 0, else the variant id
     k->gemv_variant = k->prm.tune[0] == 0 ? (quant ? 4 : 0) : (k->prm.tune[0] == 100 ? 0 : (int)k->prm.tune[0]);
-    void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t);
+    void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t, PeerStore);
     int warps, lpr;
     if (quant)
         gemv_pick<GemvS8>(k->gemv_variant, &fn, &warps, &lpr);
@@ -721,8 +721,8 @@ extern "C" size_t b200mm_kernel_workspace_bytes(const b200mm_kernel* k) { return
 extern "C" int b200mm_kernel_set_peers(b200mm_kernel* k, int rank, int world, void* const* peer_c, size_t ldc,
                                        size_t col_offset) {
     if (!k) return fail(nullptr, B200MM_ERR_INVALID, "set_peers: kern is NULL");
-    if (k->id != B200MM_K_SGEMM_SIMT && k->id != B200MM_K_SGEMM_TC3X)
-        return fail(nullptr, B200MM_ERR_INVALID, "set_peers: only the SGEMM kernels store to peers");
+    if (k->id != B200MM_K_SGEMM_SIMT && k->id != B200MM_K_SGEMM_TC3X && k->id != B200MM_K_GEMV_F32 && k->id != B200MM_K_QGEMV_SINT8)
+        return fail(nullptr, B200MM_ERR_INVALID, "set_peers: only the B200-native SGEMM / GEMV kernels store to peers");
     if (world < 0 || world > 8 || rank < 0 || (world && rank >= world)) return fail(nullptr, B200MM_ERR_INVALID, "set_peers: bad rank/world");
     if (world && (ldc % 4 || col_offset % 4)) return fail(nullptr, B200MM_ERR_INVALID, "set_peers: ldc and col_offset must be multiples of 4");
     k->peers = PeerStore{};
@@ -852,7 +852,7 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
         case B200MM_K_GEMV_F32:
         case B200MM_K_QGEMV_SINT8: {
             const bool quant = k->id == B200MM_K_QGEMV_SINT8;
-            void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t);
+            void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t, PeerStore);
             int warps, lpr;
             if (quant)
                 gemv_pick<GemvS8>(k->gemv_variant, &fn, &warps, &lpr);
@@ -860,8 +860,9 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
                 gemv_pick<GemvF32>(k->gemv_variant, &fn, &warps, &lpr);
             const float scale = quant ? k->prm.absmax / 127.0f : 1.0f;
             const size_t wstride = quant ? (size_t)K * N : (size_t)K * N * 4;
+            if (k->peers.world && (k->prm.batch > 1)) return fail(ctx, B200MM_ERR_INVALID, "peer stores are not supported for batched GEMV");
             fn<<<k->grid, k->block, k->smem, s>>>(Af, B, Cf, k->partial, k->tickets, (int)K, (int)N, k->rows_per_split, scale,
-                                                 (size_t)K, wstride, (size_t)N);
+                                                 (size_t)K, wstride, (size_t)N, k->peers);
             break;
         }
         default:

@@ -19,6 +19,7 @@
 // <= 2 ulp per output, far inside the 1e-3 gate, and is reported against FP64 in the tests.
 #pragma once
 #include "common.cuh"
+#include "sgemm_simt.cuh"  // PeerStore
 
 namespace b200mm {
 
@@ -73,6 +74,16 @@ struct GemvS8 {  // one 128-bit load = 16 int8 = 16 columns
     }
 };
 
+// N-sharded multi-GPU GEMV: this rank's y slice is also written to the same position of the full y on every
+// peer (CUDA-IPC mappings over NVLink) -- the fused form of the all-gather of y slices.
+__device__ __forceinline__ void store_y(float* y, int gc, float v, const PeerStore& peers) {
+    if (peers.world == 0) {
+        y[gc] = v;
+    } else {
+        for (int d = 0; d < peers.world; ++d) peers.c[d][peers.col0 + gc] = v;
+    }
+}
+
 // Launch: grid (panels, splits, batch), block WARPS*32.
 //   LPR   lanes per row segment (32 or 16): a warp reads 32/LPR rows per load instruction
 //   panel = LPR * COLS columns;   rows of a split are dealt round-robin to (warp, row-in-warp) slots.
@@ -81,7 +92,8 @@ template <class T, int WARPS, int UNROLL, int LPR>
 __global__ void __launch_bounds__(WARPS * 32)
 gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, float* __restrict__ y,
                    float* __restrict__ partial, unsigned int* __restrict__ tickets, int K, int N, int rows_per_split,
-                   float out_scale, size_t x_batch_stride, size_t w_batch_stride_bytes, size_t y_batch_stride) {
+                   float out_scale, size_t x_batch_stride, size_t w_batch_stride_bytes, size_t y_batch_stride,
+                   const __grid_constant__ PeerStore peers) {
     constexpr int COLS = T::COLS;
     constexpr int RPW = 32 / LPR;        // rows per warp per load
     constexpr int RSTEP = WARPS * RPW;   // rows per CTA per load
@@ -153,7 +165,7 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) s += red[(w * COLS + c % COLS) * LPR + c / COLS];
         if (splits == 1)
-            y[gc] = s * out_scale;
+            store_y(y, gc, s * out_scale, peers);
         else
             partial[pbase + (size_t)split * N + gc] = s;
     }
@@ -170,7 +182,7 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
         if (gc >= N) continue;
         float s = 0.f;
         for (int sp = 0; sp < splits; ++sp) s += __ldcg(&partial[pbase + (size_t)sp * N + gc]);
-        y[gc] = s * out_scale;
+        store_y(y, gc, s * out_scale, peers);
     }
     if (tid == 0) tickets[batch * gridDim.x + panel] = 0u;  // ready for the next launch
 }

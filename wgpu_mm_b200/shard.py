@@ -167,3 +167,95 @@ class ShardedSgemm:
         self.kern.free()
         for b in (self.A, self.Bp, self.C):
             b.free()
+
+
+class ShardedGemv:
+    """y[1 x N] = x[1 x K] * W[K x N] with W (fp32 or sint8 words) cut into `world` column panels (SURVEY 8e:
+    "weight rows" in the LLM out x in convention are columns of the reference's K x N matrix, Q3).  x is replicated,
+    every rank ends the step holding the full y.  fused: the kernel's final store writes the slice into y on every
+    rank through CUDA-IPC peer mappings; nccl: local slice + all_gather_into_tensor (slices are contiguous)."""
+
+    def __init__(self, ctx, K: int, N: int, plan: ShardPlan, quant: bool = False, mode: str = "fused", seed: int = 300,
+                 x_host=None, panel_host=None, absmax: float = 2.0):
+        import torch
+        import torch.distributed as dist
+        import wgpu_mm_b200 as w
+
+        self.torch, self.dist, self.w = torch, dist, w
+        self.ctx, self.K, self.N, self.plan, self.mode, self.quant = ctx, K, N, plan, mode, quant
+        self.stream = torch.cuda.Stream()
+        torch.cuda.set_stream(self.stream)
+        ctx.set_stream(self.stream.cuda_stream)
+        Np = plan.cols
+        if quant and Np % 16:
+            raise ValueError("sint8 panels must be a multiple of 16 columns")
+        self.x = ctx.buffer_from(x_host) if x_host is not None else ctx.buffer(K * 4)
+        if x_host is None:
+            self.x.fill_weights(seed + 1, K)
+        if panel_host is not None:
+            self.W = ctx.buffer_from(panel_host)
+        elif quant:
+            self.W = ctx.buffer(K * Np)
+            self.W.fill_weights(seed + 2 + plan.rank, K * Np // 4)  # arbitrary bytes: bandwidth measurements only
+        else:
+            self.W = ctx.buffer(K * Np * 4)
+            self.W.fill_weights_2d(seed + 2, K, Np, N, plan.col0)
+        self.y = ctx.buffer(N * 4)
+        self.peers = []
+        self._flag = torch.zeros(1, device="cuda")
+        kid = w.KernelId.QGEMV_SINT8 if quant else w.KernelId.GEMV_F32
+        self.kern = ctx.kernel(kid, 1, Np, K, w.KernelParams(absmax=absmax, batch=1))
+        if mode == "fused":
+            handles = [None] * plan.world
+            dist.all_gather_object(handles, self.y.ipc_export())
+            ptrs = []
+            for r in range(plan.world):
+                if r == plan.rank:
+                    ptrs.append(self.y.ptr)
+                else:
+                    pb = ctx.ipc_import(handles[r], N * 4)
+                    self.peers.append(pb)
+                    ptrs.append(pb.ptr)
+            self.kern.set_peers(plan.rank, plan.world, ptrs, N, plan.col0)
+        elif mode == "nccl":
+            self.ys_t = torch.empty(Np, dtype=torch.float32, device="cuda")
+            self.yg_t = torch.empty(N, dtype=torch.float32, device="cuda")
+            self.ys = ctx.wrap(self.ys_t.data_ptr(), Np * 4)
+            self.yg = ctx.wrap(self.yg_t.data_ptr(), N * 4)
+        else:
+            raise ValueError(mode)
+        self.kern.profile(True)
+        ctx.sync()
+        dist.barrier()
+
+    def step(self):
+        if self.mode == "fused":
+            self.ctx.launch(self.kern, self.x, self.W, self.y)
+            self.dist.all_reduce(self._flag)  # all ranks' stores of this step are issued before anyone starts the next
+        else:
+            self.ctx.launch(self.kern, self.x, self.W, self.ys)
+            self.dist.all_gather_into_tensor(self.yg_t, self.ys_t)
+
+    def result(self) -> np.ndarray:
+        self.barrier()
+        return (self.y if self.mode == "fused" else self.yg).read(np.float32, count=self.N)
+
+    def barrier(self):
+        self.ctx.sync()
+        self.torch.cuda.synchronize()
+        self.dist.barrier()
+
+    def kernel_times(self):
+        return self.kern.profile_read(256)
+
+    def bytes_per_rank(self) -> int:
+        Np = self.plan.cols
+        return (self.K * Np if self.quant else 4 * self.K * Np) + 4 * self.K + 4 * Np
+
+    def close(self):
+        self.barrier()
+        for b in self.peers:
+            b.free()
+        self.kern.free()
+        for b in (self.x, self.W, self.y):
+            b.free()
