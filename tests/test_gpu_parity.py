@@ -81,10 +81,13 @@ def test_sgemm_simt_aligned(gpu_ctx, oracle, shape):
     M, N, K = shape
     A = oracle.generate_weight_data(5, M, K)
     B = oracle.generate_weight_data(6, K, N)
-    got = _run(gpu_ctx, w.KernelId.SGEMM_SIMT, A, B, M, N, K)
+    got = _run(gpu_ctx, w.KernelId.SGEMM_SIMT, A, B, M, N, K)  # default schedule: leftover tiles are split along K
     _check(oracle, got, A, B)
-    # k-sequential fma per output == gemm_5.wgsl's order == oracle_wgsl_gemm_3 (same arithmetic, no tiling simulated)
-    assert np.array_equal(got, oracle.wgsl_gemm("gemm_3", A, B))
+    again = _run(gpu_ctx, w.KernelId.SGEMM_SIMT, A, B, M, N, K)
+    assert np.array_equal(got, again), "split-K parts are added in a fixed order: results must be deterministic"
+    # B200MM_F_SEQUENTIAL_K: k-sequential fma per output == gemm_5.wgsl's order == oracle_wgsl_gemm_3 (same arithmetic)
+    seq = _run(gpu_ctx, w.KernelId.SGEMM_SIMT, A, B, M, N, K, w.KernelParams(flags=int(w.Flags.SEQUENTIAL_K)))
+    assert np.array_equal(seq, oracle.wgsl_gemm("gemm_3", A, B))
 
 
 @pytest.mark.parametrize("shape", [(1, 4, 4), (5, 7, 3), (130, 257, 45), (127, 129, 17), (300, 100, 1000)])

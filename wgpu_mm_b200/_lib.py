@@ -42,6 +42,7 @@ class Flags(enum.IntFlag):
     NONE = 0
     TC3X_1X = 0x1
     PEER_STORE = 0x2
+    SEQUENTIAL_K = 0x4
 
 
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_LIMITS, ERR_UNSUPPORTED, ERR_TOLERANCE = -1, -2, -3, -4, -5, -6

@@ -69,6 +69,9 @@ struct b200mm_kernel {
     int splits = 1, rows_per_split = 0, panels = 0, gemv_variant = 0;
     float* partial = nullptr;
     unsigned int* tickets = nullptr;
+    // simt schedule: launch 1 = simt_tiles1 whole tiles, launch 2 = simt_tiles2 tiles x simt.split K-parts
+    SimtSched simt{};
+    int simt_tiles1 = 0, simt_tiles2 = 0;
     // multi-GPU
     PeerStore peers{};
     // per-launch profiling of the dominant kernel
@@ -503,8 +506,39 @@ static int setup_ports(b200mm_ctx* ctx, b200mm_kernel* k) {
 static int setup_simt(b200mm_ctx* ctx, b200mm_kernel* k) {
     if (k->M > INT32_MAX || k->N > INT32_MAX || k->K > INT32_MAX) return fail(ctx, B200MM_ERR_INVALID, "shape too large");
     k->block = dim3(SimtCfg::THREADS, 1, 1);
-    k->grid = dim3(ceil_div(k->M, SimtCfg::BM), ceil_div(k->N, SimtCfg::BN), 1);
-    if (k->grid.y > 65535) return fail(ctx, B200MM_ERR_LIMITS, "Compute limits exceeded");
+    const long long tiles_m = (long long)ceil_div(k->M, SimtCfg::BM), tiles_n = (long long)ceil_div(k->N, SimtCfg::BN);
+    const long long tiles = tiles_m * tiles_n;
+    if (tiles > INT32_MAX) return fail(ctx, B200MM_ERR_LIMITS, "Compute limits exceeded");
+    // 2 resident CTAs per SM (registers); see SimtSched for the two-launch schedule
+    const long long slots = (long long)ctx->prop.multiProcessorCount * 2;
+    SimtSched& sc = k->simt;
+    sc.tiles_m = (int)tiles_m;
+    sc.tiles_n = (int)tiles_n;
+    sc.group_m = k->prm.tune[1] ? (int)k->prm.tune[1] : 16;
+    sc.split = 1;
+    const int KT = (int)ceil_div(k->K, SimtCfg::BK);
+    const bool seq_k = (k->prm.flags & B200MM_F_SEQUENTIAL_K) != 0;
+    // Measured on B200 (tools/bench_simt.py): once every SM has a tile, splitting the tiles of a partial last wave
+    // buys nothing (one CTA per SM sustains the same FMA rate as two), so K is split only when there are fewer
+    // tiles than resident CTAs (e.g. 1024^3 = 64 tiles -> 4 K-parts each).
+    long long rem = tiles < slots ? tiles : 0;
+    int split = 1;
+    if (!seq_k && rem > 0) split = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(slots / rem, 8), KT / 4));
+    if (split <= 1) rem = 0;  // nothing to gain: one launch over all tiles
+    k->simt_tiles1 = (int)(tiles - rem);
+    k->simt_tiles2 = (int)rem;
+    sc.split = split;
+    k->grid = dim3((unsigned)std::max<long long>(k->simt_tiles1, rem * split), 1, 1);
+    if (rem > 0) {
+        const size_t n_cta2 = (size_t)rem * split;
+        const size_t part_bytes = n_cta2 * SimtCfg::BM * SimtCfg::BN * sizeof(float);
+        const size_t flag_bytes = ceil_div(n_cta2 * sizeof(unsigned int), 256) * 256;
+        k->ws_bytes = part_bytes + flag_bytes;
+        CU_TRY(ctx, cudaMalloc(&k->ws, k->ws_bytes));
+        CU_TRY(ctx, cudaMemsetAsync(k->ws, 0, k->ws_bytes, ctx->stream));
+        sc.partial = (float4*)k->ws;
+        sc.flags = (unsigned int*)((char*)k->ws + part_bytes);
+    }
     return B200MM_OK;
 }
 
@@ -803,11 +837,20 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
             break;
         case B200MM_K_SGEMM_SIMT: {
             const bool aligned = (M % SimtCfg::BM == 0) && (N % SimtCfg::BN == 0) && (K % SimtCfg::BK == 0);
-            if (aligned)
-                sgemm_simt_kernel<false><<<k->grid, k->block, 0, s>>>(Af, Bf, Cf, (int)M, (int)N, (int)K, (int)N, k->peers);
-            else {
-                if (k->peers.world) return fail(ctx, B200MM_ERR_INVALID, "peer stores need tile-aligned shapes");
-                sgemm_simt_kernel<true><<<k->grid, k->block, 0, s>>>(Af, Bf, Cf, (int)M, (int)N, (int)K, (int)N, k->peers);
+            k->simt.epoch++;
+            if (!aligned && k->peers.world) return fail(ctx, B200MM_ERR_INVALID, "peer stores need tile-aligned shapes");
+            for (int pass = 0; pass < 2; ++pass) {
+                SimtSched sc = k->simt;
+                const int ntiles = pass == 0 ? k->simt_tiles1 : k->simt_tiles2;
+                if (ntiles == 0) continue;
+                sc.tile_offset = pass == 0 ? 0 : k->simt_tiles1;
+                sc.split = pass == 0 ? 1 : k->simt.split;
+                const dim3 g((unsigned)ntiles * sc.split, 1, 1);
+                if (aligned)
+                    sgemm_simt_kernel<false><<<g, k->block, 0, s>>>(Af, Bf, Cf, (int)M, (int)N, (int)K, (int)N, k->peers, sc);
+                else
+                    sgemm_simt_kernel<true><<<g, k->block, 0, s>>>(Af, Bf, Cf, (int)M, (int)N, (int)K, (int)N, k->peers, sc);
+                if (pass == 1 && k->simt_tiles1) ctx->launches++;
             }
             break;
         }

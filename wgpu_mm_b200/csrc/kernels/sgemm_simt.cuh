@@ -10,8 +10,10 @@
 //                          A staged transposed so both fragments are float4 reads.
 //
 // Accumulation per output is k-sequential fma in fp32, i.e. exactly gemm_5.wgsl's order
-// (threadResults = fma(regM, regN, threadResults), :74-76), so results agree with the
-// oracle_wgsl_gemm_5 restatement bit for bit when K % 16 == 0.
+// (threadResults = fma(regM, regN, threadResults), :74-76): with B200MM_F_SEQUENTIAL_K results agree with the
+// oracle_wgsl_gemm_5 restatement bit for bit (always the case when there are at least 2 tiles per SM).  Small problems
+// are split along K over otherwise idle SMs; the parts are added in a fixed order, so the result is deterministic but
+// rounds differently from a single k-sequential chain.
 //
 // Data layout: A (M x K), B (K x N), C (M x N) row-major f32 in HBM; nothing is transposed or padded
 // in global memory.  Shapes that are not multiples of the tile go through the guarded instantiation.
@@ -33,6 +35,19 @@ struct SimtCfg {
 
 // Optional fused all-gather: every finished row segment is also stored to the same (row, col) of the
 // full C on each peer GPU (NVLink peer mappings), see b200mm_kernel_set_peers.
+// Schedule.  One CTA per tile (hardware block scheduler, 2 CTAs resident per SM).  When a problem has fewer tiles
+// than resident CTAs, each tile is cut into `split` K-parts (CTA = tile * split + part) so that all SMs have work.
+// Part 0 owns the tile: it adds the partial tiles the other parts parked in `partial` (flag = epoch) in part order
+// (deterministic) and stores C.  All CTAs of such a launch are co-resident, so the owner's wait cannot deadlock.
+// (Measured and rejected: a persistent loop -- extra live state pushed the main loop over the 128-register budget and
+// ptxas sank the prefetch; splitting only the partial last wave of a large problem -- no gain.)
+struct SimtSched {
+    int tiles_m, tiles_n, group_m, tile_offset, split;
+    float4* partial;        // [gridDim.x][BM*BN/4]
+    unsigned int* flags;    // [gridDim.x]
+    unsigned int epoch;
+};
+
 struct PeerStore {
     float* c[8];
     int world;     // 0 = disabled
@@ -44,7 +59,7 @@ struct PeerStore {
 template <bool GUARD>
 __global__ void __launch_bounds__(SimtCfg::THREADS, 2)
 sgemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K,
-                  int ldc, const __grid_constant__ PeerStore peers) {
+                  int ldc, const __grid_constant__ PeerStore peers, const __grid_constant__ SimtSched sched) {
     using Cfg = SimtCfg;
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, AS_LD = Cfg::AS_LD, BS_LD = Cfg::BS_LD;
     __shared__ __align__(16) float smem[Cfg::SMEM_FLOATS];
@@ -56,122 +71,177 @@ sgemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, floa
     // 8 warps as 2 (m) x 4 (n); warp tile 64 x 32; lanes as 8 (m) x 4 (n); thread patch = 2 x 2 blocks of 4 x 4
     const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
     const int tm = (lane >> 2) * 4, tn = (lane & 3) * 4;
-
-    // consecutive blockIdx.x walk down M inside a 128-column panel of B so that panel stays L2/L1-hot
-    const int block_m = blockIdx.x * BM, block_n = blockIdx.y * BN;
-
     // global -> register staging: A tile 128 x 16 = 512 float4 (2 per thread), B tile 16 x 128 = 512 float4
-    const int a_row = tid >> 2, a_kq = (tid & 3) * 4;  // rows a_row and a_row + 64
+    const int a_row = tid >> 2, a_kq = (tid & 3) * 4;    // rows a_row and a_row + 64
     const int b_row = tid >> 5, b_col = (tid & 31) * 4;  // rows b_row and b_row + 8
-    const float* Ag = A + (size_t)(block_m + a_row) * K + a_kq;
-    const float* Bg = B + (size_t)b_row * N + block_n + b_col;
+    const int KT = (K + BK - 1) / BK;
 
-    float4 ra[2], rb[2];
-    auto load_tile = [&](int k0) {
-        if constexpr (!GUARD) {
-            ra[0] = __ldg(reinterpret_cast<const float4*>(Ag + k0));
-            ra[1] = __ldg(reinterpret_cast<const float4*>(Ag + (size_t)64 * K + k0));
-            rb[0] = __ldg(reinterpret_cast<const float4*>(Bg + (size_t)k0 * N));
-            rb[1] = __ldg(reinterpret_cast<const float4*>(Bg + (size_t)(k0 + 8) * N));
-        } else {
+    // grouped rasterisation (bands of 16 tile rows) so the tiles in flight share operand panels in L2
+    auto tile_coords = [&](int t, int& bm, int& bn) {
+        const int GROUP_M = sched.group_m;
+        const int band_tiles = GROUP_M * sched.tiles_n;
+        const int band = t / band_tiles;
+        const int first_m = band * GROUP_M;
+        const int rows = min(GROUP_M, sched.tiles_m - first_m);
+        const int r = t - band * band_tiles;
+        bm = (first_m + r % rows) * BM;
+        bn = (r / rows) * BN;
+    };
+
+    {
+        const int tile = sched.tile_offset + (int)blockIdx.x / sched.split;
+        const int part = (int)blockIdx.x % sched.split, nparts = sched.split;
+        int block_m, block_n;
+        tile_coords(tile, block_m, block_n);
+        const int kt_begin = (int)((long long)part * KT / nparts), kt_end = (int)((long long)(part + 1) * KT / nparts);
+
+        const float* Ag = A + (size_t)(block_m + a_row) * K + a_kq;
+        const float* Bg = B + (size_t)b_row * N + block_n + b_col;
+        float4 ra[2], rb[2];
+        // A goes through registers (it is transposed on the way into shared memory); in the aligned instantiation B is
+        // copied global -> shared by cp.async straight into the NEXT buffer, so the prefetch needs no registers and cannot
+        // be sunk below the FMA block by the compiler (which it did, at the 128-register cap, with a register-staged B).
+        auto load_tile = [&](int k0, int nbuf) {
+            if constexpr (!GUARD) {
+                ra[0] = __ldg(reinterpret_cast<const float4*>(Ag + k0));
+                ra[1] = __ldg(reinterpret_cast<const float4*>(Ag + (size_t)64 * K + k0));
+                const uint32_t dst = smem_u32(Bs0 + nbuf * (BK * BS_LD) + b_row * BS_LD + b_col);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(Bg + (size_t)k0 * N) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 8 * BS_LD * 4), "l"(Bg + (size_t)(k0 + 8) * N) : "memory");
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float v[4];
+                    const int r = block_m + a_row + 64 * h;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = k0 + a_kq + j;
+                        v[j] = (r < M && k < K) ? A[(size_t)r * K + k] : 0.f;
+                    }
+                    ra[h] = make_float4(v[0], v[1], v[2], v[3]);
+                    const int kb = k0 + b_row + 8 * h;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = block_n + b_col + j;
+                        v[j] = (kb < K && c < N) ? B[(size_t)kb * N + c] : 0.f;
+                    }
+                    rb[h] = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
+        };
+        auto store_tile = [&](int buf) {
+            float* as = As0 + buf * (BK * AS_LD);
+            float* bs = Bs0 + buf * (BK * BS_LD);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                float v[4];
-                const int r = block_m + a_row + 64 * h;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int k = k0 + a_kq + j;
-                    v[j] = (r < M && k < K) ? A[(size_t)r * K + k] : 0.f;
-                }
-                ra[h] = make_float4(v[0], v[1], v[2], v[3]);
-                const int kb = k0 + b_row + 8 * h;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = block_n + b_col + j;
-                    v[j] = (kb < K && c < N) ? B[(size_t)kb * N + c] : 0.f;
-                }
-                rb[h] = make_float4(v[0], v[1], v[2], v[3]);
+                const int r = a_row + 64 * h;
+                as[(a_kq + 0) * AS_LD + r] = ra[h].x;
+                as[(a_kq + 1) * AS_LD + r] = ra[h].y;
+                as[(a_kq + 2) * AS_LD + r] = ra[h].z;
+                as[(a_kq + 3) * AS_LD + r] = ra[h].w;
+                if constexpr (GUARD) *reinterpret_cast<float4*>(&bs[(b_row + 8 * h) * BS_LD + b_col]) = rb[h];
             }
+            if constexpr (!GUARD) asm volatile("cp.async.wait_all;" ::: "memory");
+        };
+
+        float acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+        if (kt_begin < kt_end) {
+            load_tile(kt_begin * BK, 0);
+            store_tile(0);
         }
-    };
-    auto store_tile = [&](int buf) {
-        float* as = As0 + buf * (BK * AS_LD);
-        float* bs = Bs0 + buf * (BK * BS_LD);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int r = a_row + 64 * h;
-            as[(a_kq + 0) * AS_LD + r] = ra[h].x;
-            as[(a_kq + 1) * AS_LD + r] = ra[h].y;
-            as[(a_kq + 2) * AS_LD + r] = ra[h].z;
-            as[(a_kq + 3) * AS_LD + r] = ra[h].w;
-            *reinterpret_cast<float4*>(&bs[(b_row + 8 * h) * BS_LD + b_col]) = rb[h];
-        }
-    };
+        __syncthreads();
 
-    float acc[8][8];
+        for (int kt = kt_begin; kt < kt_end; ++kt) {
+            const int buf = (kt - kt_begin) & 1;
+            if (kt + 1 < kt_end) load_tile((kt + 1) * BK, buf ^ 1);  // global loads in flight across the whole k-tile
+            const float* as = As0 + buf * (BK * AS_LD) + wm + tm;
+            const float* bs = Bs0 + buf * (BK * BS_LD) + wn + tn;
+            float4 fa[2][2], fb[2][2];  // register double buffer for the fragments
+            fa[0][0] = *reinterpret_cast<const float4*>(as);
+            fa[0][1] = *reinterpret_cast<const float4*>(as + 32);
+            fb[0][0] = *reinterpret_cast<const float4*>(bs);
+            fb[0][1] = *reinterpret_cast<const float4*>(bs + 16);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+            for (int k = 0; k < BK; ++k) {
+                const int cur = k & 1, nxt = cur ^ 1;
+                if (k + 1 < BK) {
+                    fa[nxt][0] = *reinterpret_cast<const float4*>(as + (k + 1) * AS_LD);
+                    fa[nxt][1] = *reinterpret_cast<const float4*>(as + (k + 1) * AS_LD + 32);
+                    fb[nxt][0] = *reinterpret_cast<const float4*>(bs + (k + 1) * BS_LD);
+                    fb[nxt][1] = *reinterpret_cast<const float4*>(bs + (k + 1) * BS_LD + 16);
+                }
+                const float a[8] = {fa[cur][0].x, fa[cur][0].y, fa[cur][0].z, fa[cur][0].w,
+                                    fa[cur][1].x, fa[cur][1].y, fa[cur][1].z, fa[cur][1].w};
+                const float b[8] = {fb[cur][0].x, fb[cur][0].y, fb[cur][0].z, fb[cur][0].w,
+                                    fb[cur][1].x, fb[cur][1].y, fb[cur][1].z, fb[cur][1].w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-
-    const int KT = (K + BK - 1) / BK;
-    load_tile(0);
-    store_tile(0);
-    __syncthreads();
-
-    for (int kt = 0; kt < KT; ++kt) {
-        const int buf = kt & 1;
-        if (kt + 1 < KT) load_tile((kt + 1) * BK);  // global loads in flight across the whole k-tile
-        const float* as = As0 + buf * (BK * AS_LD) + wm + tm;
-        const float* bs = Bs0 + buf * (BK * BS_LD) + wn + tn;
-        float4 fa[2][2], fb[2][2];  // register double buffer for the fragments
-        fa[0][0] = *reinterpret_cast<const float4*>(as);
-        fa[0][1] = *reinterpret_cast<const float4*>(as + 32);
-        fb[0][0] = *reinterpret_cast<const float4*>(bs);
-        fb[0][1] = *reinterpret_cast<const float4*>(bs + 16);
+                for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int k = 0; k < BK; ++k) {
-            const int cur = k & 1, nxt = cur ^ 1;
-            if (k + 1 < BK) {
-                fa[nxt][0] = *reinterpret_cast<const float4*>(as + (k + 1) * AS_LD);
-                fa[nxt][1] = *reinterpret_cast<const float4*>(as + (k + 1) * AS_LD + 32);
-                fb[nxt][0] = *reinterpret_cast<const float4*>(bs + (k + 1) * BS_LD);
-                fb[nxt][1] = *reinterpret_cast<const float4*>(bs + (k + 1) * BS_LD + 16);
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
             }
-            const float a[8] = {fa[cur][0].x, fa[cur][0].y, fa[cur][0].z, fa[cur][0].w,
-                                fa[cur][1].x, fa[cur][1].y, fa[cur][1].z, fa[cur][1].w};
-            const float b[8] = {fb[cur][0].x, fb[cur][0].y, fb[cur][0].z, fb[cur][0].w,
-                                fb[cur][1].x, fb[cur][1].y, fb[cur][1].z, fb[cur][1].w};
+            if (kt + 1 < kt_end) store_tile(buf ^ 1);
+            __syncthreads();
+        }
+
+        if (part != 0) {
+            // K-part of a split tile: park the partial tile for the owner (thread-major float4 layout, coalesced)
+            float4* slot = sched.partial + (size_t)blockIdx.x * (BM * BN / 4);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int h = 0; h < 2; ++h)
+                    slot[(i * 2 + h) * Cfg::THREADS + tid] = make_float4(acc[i][4 * h + 0], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(sched.flags + blockIdx.x), "r"(sched.epoch) : "memory");
+            return;
         }
-        if (kt + 1 < KT) store_tile(buf ^ 1);
-        __syncthreads();
-    }
-
-    // epilogue: rows {tm..tm+3, 32+tm..}, cols {tn..tn+3, 16+tn..} of the warp tile; float4 stores
+        for (int pp = 1; pp < nparts; ++pp) {
+            // owner: add the other parts in part order (deterministic)
+            unsigned int seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sched.flags + blockIdx.x + pp) : "memory");
+            } while (seen != sched.epoch);
+            const float4* slot = sched.partial + (size_t)(blockIdx.x + pp) * (BM * BN / 4);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = block_m + wm + tm + (i & 3) + (i >> 2) * 32;
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int c = block_n + wn + tn + h * 16;
-            const float4 v = make_float4(acc[i][4 * h + 0], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]);
-            if constexpr (!GUARD) {
-                if (peers.world == 0) {
-                    *reinterpret_cast<float4*>(&C[(size_t)r * ldc + c]) = v;
-                } else {
-#pragma unroll 1
-                    for (int p = 0; p < peers.world; ++p)
-                        *reinterpret_cast<float4*>(&peers.c[p][(size_t)r * peers.ldc + peers.col0 + c]) = v;
+                for (int h = 0; h < 2; ++h) {
+                    const float4 w = __ldcg(slot + (i * 2 + h) * Cfg::THREADS + tid);
+                    acc[i][4 * h + 0] += w.x;
+                    acc[i][4 * h + 1] += w.y;
+                    acc[i][4 * h + 2] += w.z;
+                    acc[i][4 * h + 3] += w.w;
                 }
-            } else {
-                const float e[4] = {v.x, v.y, v.z, v.w};
+        }
+
+        // epilogue: rows {tm..tm+3, 32+tm..}, cols {tn..tn+3, 16+tn..} of the warp tile; float4 stores
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (r < M && c + j < N) C[(size_t)r * ldc + c + j] = e[j];
+        for (int i = 0; i < 8; ++i) {
+            const int r = block_m + wm + tm + (i & 3) + (i >> 2) * 32;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = block_n + wn + tn + h * 16;
+                const float4 v = make_float4(acc[i][4 * h + 0], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]);
+                if constexpr (!GUARD) {
+                    if (peers.world == 0) {
+                        *reinterpret_cast<float4*>(&C[(size_t)r * ldc + c]) = v;
+                    } else {
+#pragma unroll 1
+                        for (int p = 0; p < peers.world; ++p)
+                            *reinterpret_cast<float4*>(&peers.c[p][(size_t)r * peers.ldc + peers.col0 + c]) = v;
+                    }
+                } else {
+                    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (r < M && c + j < N) C[(size_t)r * ldc + c + j] = e[j];
+                }
             }
         }
     }
