@@ -167,7 +167,7 @@ def test_sgemm_linearity_full_size(gpu_ctx):
 GEMV_SHAPES = [(64, 64), (512, 1024), (1000, 260), (4096, 16384), (36, 4)]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 100, 1, 2, 3, 4, 6, 7])
 @pytest.mark.parametrize("kn", GEMV_SHAPES)
 def test_gemv_f32(gpu_ctx, oracle, kn, variant):
     """fp32 GEMV vs mm_ref with M == 1 (the reference has no fp32 GEMV shader)."""
@@ -179,13 +179,15 @@ def test_gemv_f32(gpu_ctx, oracle, kn, variant):
     _check(oracle, got, x, W)
 
 
-@pytest.mark.parametrize("splits", [1, 2, 7, 64])
-def test_gemv_f32_split_k_is_deterministic(gpu_ctx, oracle, splits):
+@pytest.mark.parametrize("cluster_off", [0, 1])
+@pytest.mark.parametrize("splits", [1, 2, 7, 8, 64])
+def test_gemv_f32_split_k_is_deterministic(gpu_ctx, oracle, splits, cluster_off):
     import wgpu_mm_b200 as w
     K, N = 2048, 1024
     x = oracle.generate_weight_data(19, 1, K)
     W = oracle.generate_weight_data(20, K, N)
-    prm = w.KernelParams(tune=(0, splits, 0, 0))
+    # splits <= 8 are reduced inside a thread-block cluster (DSMEM); cluster_off = 1 or splits > 8 use the ticket path
+    prm = w.KernelParams(tune=(0, splits, 0, cluster_off))
     a = _run(gpu_ctx, w.KernelId.GEMV_F32, x, W, 1, N, K, prm)
     b = _run(gpu_ctx, w.KernelId.GEMV_F32, x, W, 1, N, K, prm)
     assert np.array_equal(a, b)
@@ -195,7 +197,7 @@ def test_gemv_f32_split_k_is_deterministic(gpu_ctx, oracle, splits):
 QSHAPES = [(1024, 1024), (64, 64), (4096, 14336), (200, 48), (36, 16)]
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 100, 1, 5, 6])
 @pytest.mark.parametrize("kn", QSHAPES)
 def test_qgemv_sint8(gpu_ctx, oracle, kn, variant):
     """Quantised GEMV in the src/quant.rs format with the reference's ABSMAX = 2.0 quirk."""

@@ -67,6 +67,7 @@ struct b200mm_kernel {
     long long tc_sk_units = 0;
     // gemv
     int splits = 1, rows_per_split = 0, panels = 0, gemv_variant = 0;
+    bool gemv_cluster = false;
     float* partial = nullptr;
     unsigned int* tickets = nullptr;
     // simt schedule: launch 1 = simt_tiles1 whole tiles, launch 2 = simt_tiles2 tiles x simt.split K-parts
@@ -388,7 +389,7 @@ using Tc256x1 = Tc3xCfg<256, 4, true, 32>;
 // gemv variants: 0: 8 warps, unroll 8, full-warp rows;  1: 8 warps, unroll 8, half-warp rows
 template <class T>
 static void gemv_pick(int variant, void (**fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float,
-                                               size_t, size_t, size_t, PeerStore),
+                                               size_t, size_t, size_t, PeerStore, int),
                       int* warps, int* lpr) {
     if (variant == 1) {
         *fn = gemv_stream_kernel<T, 8, 8, 16>;
@@ -620,8 +621,8 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
         return fail(ctx, B200MM_ERR_INVALID, "%s needs N%%%d==0 and K%%4==0", b200mm_kernel_name(k->id), cols);
     if (N > INT32_MAX || K > INT32_MAX) return fail(ctx, B200MM_ERR_INVALID, "shape too large");
     // tune[0]: 0 = default for the weight type (measured on B200, tools/sweep_gemv.py), 100 = variant 0, else the variant id
-    k->gemv_variant = k->prm.tune[0] == 0 ? (quant ? 4 : 0) : (k->prm.tune[0] == 100 ? 0 : (int)k->prm.tune[0]);
-    void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t, PeerStore);
+    k->gemv_variant = k->prm.tune[0] == 0 ? (quant ? 4 : 5) : (k->prm.tune[0] == 100 ? 0 : (int)k->prm.tune[0]);
+    void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t, PeerStore, int);
     int warps, lpr;
     if (quant)
         gemv_pick<GemvS8>(k->gemv_variant, &fn, &warps, &lpr);
@@ -645,6 +646,14 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
         splits = std::max(1, std::min(splits, 64));
         splits = (int)std::min<size_t>(splits, std::max<size_t>(1, K / 32));
     }
+    // K-splits of a panel are reduced inside a thread-block cluster (<= 8 CTAs, portable size) unless tune[3] == 1
+    k->gemv_cluster = (k->prm.tune[3] != 1);
+    if (k->gemv_cluster && splits > 8) {
+        if (k->prm.tune[1] > 0)
+            k->gemv_cluster = false;  // an explicit split count above 8 keeps the ticket path
+        else
+            splits = 8;
+    }
     const int rstep = warps * (32 / lpr);
     size_t rps = ceil_div(K, (size_t)splits);
     rps = ceil_div(rps, rstep) * rstep;
@@ -653,10 +662,10 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     k->rows_per_split = (int)rps;
     k->grid = dim3(k->panels, splits, batch);
     k->block = dim3(warps * 32, 1, 1);
-    k->smem = (rps + (size_t)warps * panel) * sizeof(float);
+    k->smem = (rps + (size_t)warps * panel + panel) * sizeof(float);
     if (k->smem > 200 * 1024) return fail(ctx, B200MM_ERR_INVALID, "gemv: K-split too long for shared memory");
     CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(k->smem, 48 * 1024)));
-    if (splits > 1) {
+    if (splits > 1 && !k->gemv_cluster) {
         const size_t pbytes = (size_t)batch * splits * N * sizeof(float);
         const size_t tbytes = (size_t)batch * k->panels * sizeof(unsigned int);
         k->ws_bytes = ceil_div(pbytes, 256) * 256 + tbytes;
@@ -895,7 +904,7 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
         case B200MM_K_GEMV_F32:
         case B200MM_K_QGEMV_SINT8: {
             const bool quant = k->id == B200MM_K_QGEMV_SINT8;
-            void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t, PeerStore);
+            void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t, PeerStore, int);
             int warps, lpr;
             if (quant)
                 gemv_pick<GemvS8>(k->gemv_variant, &fn, &warps, &lpr);
@@ -904,8 +913,27 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
             const float scale = quant ? k->prm.absmax / 127.0f : 1.0f;
             const size_t wstride = quant ? (size_t)K * N : (size_t)K * N * 4;
             if (k->peers.world && (k->prm.batch > 1)) return fail(ctx, B200MM_ERR_INVALID, "peer stores are not supported for batched GEMV");
-            fn<<<k->grid, k->block, k->smem, s>>>(Af, B, Cf, k->partial, k->tickets, (int)K, (int)N, k->rows_per_split, scale,
-                                                 (size_t)K, wstride, (size_t)N, k->peers);
+            // launched with programmatic stream serialization (PDL): see the griddepcontrol comments in gemv.cuh
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = k->grid;
+            cfg.blockDim = k->block;
+            cfg.dynamicSmemBytes = k->smem;
+            cfg.stream = s;
+            cudaLaunchAttribute attr[2];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = (k->prm.tune[2] == 1) ? 0 : 1;  // tune[2] = 1 disables PDL
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            const bool cluster = k->gemv_cluster && k->splits > 1;
+            if (cluster) {
+                attr[1].id = cudaLaunchAttributeClusterDimension;
+                attr[1].val.clusterDim.x = 1;
+                attr[1].val.clusterDim.y = (unsigned)k->splits;
+                attr[1].val.clusterDim.z = 1;
+                cfg.numAttrs = 2;
+            }
+            CU_TRY(ctx, cudaLaunchKernelEx(&cfg, fn, Af, (const void*)B, Cf, k->partial, k->tickets, (int)K, (int)N, k->rows_per_split, scale,
+                                           (size_t)K, wstride, (size_t)N, k->peers, cluster ? 1 : 0));
             break;
         }
         default:

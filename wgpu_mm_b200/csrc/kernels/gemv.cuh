@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(WARPS * 32)
 gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, float* __restrict__ y,
                    float* __restrict__ partial, unsigned int* __restrict__ tickets, int K, int N, int rows_per_split,
                    float out_scale, size_t x_batch_stride, size_t w_batch_stride_bytes, size_t y_batch_stride,
-                   const __grid_constant__ PeerStore peers) {
+                   const __grid_constant__ PeerStore peers, int use_cluster) {
     constexpr int COLS = T::COLS;
     constexpr int RPW = 32 / LPR;        // rows per warp per load
     constexpr int RSTEP = WARPS * RPW;   // rows per CTA per load
@@ -116,6 +116,25 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
 
     const int k_beg = split * rows_per_split;
     const int k_end = min(K, k_beg + rows_per_split);
+    const char* wp = Wb + (size_t)col / COLS * sizeof(typename T::Vec);
+    int k = k_beg + warp * RPW + riw;
+
+    // Software pipeline: the loads of batch i+1 are issued before batch i is consumed, and the very first batch is
+    // issued BEFORE x is staged, so its DRAM latency overlaps the staging barrier (every serialized ~1 us matters in
+    // a kernel whose ideal duration is ~10 us).
+    // Programmatic dependent launch: let the next kernel in the stream start as soon as SM resources free up, and do
+    // not touch anything a previous kernel may still produce (x, partials, tickets, y) before griddepcontrol.wait.
+    // The weights never depend on the previous kernel, so their first loads overlap its tail (no-ops without PDL).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    typename T::Vec wa[UNROLL], wb[UNROLL];
+    auto issue = [&](typename T::Vec (&w)[UNROLL], int kk) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+            if (col_ok && kk + u * RSTEP < k_end) w[u] = T::load(wp + (size_t)(kk + u * RSTEP) * row_pitch);
+    };
+    issue(wa, k);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
     for (int i = tid; i < rows_per_split; i += WARPS * 32) xs[i] = (k_beg + i < k_end) ? x[k_beg + i] : 0.f;
     __syncthreads();
 
@@ -123,25 +142,16 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
 #pragma unroll
     for (int j = 0; j < COLS; ++j) acc[j] = 0.f;
 
-    const char* wp = Wb + (size_t)col / COLS * sizeof(typename T::Vec);
-    int k = k_beg + warp * RPW + riw;
-    // main loop: UNROLL independent 128-bit loads in flight per thread
-    for (; k + (UNROLL - 1) * RSTEP < k_end; k += UNROLL * RSTEP) {
-        typename T::Vec w[UNROLL];
+    auto consume = [&](const typename T::Vec (&w)[UNROLL], int kk) {
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            if (col_ok) w[u] = T::load(wp + (size_t)(k + u * RSTEP) * row_pitch);
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            if (col_ok) T::fma(acc, w[u], xs[k + u * RSTEP - k_beg]);
-        }
-    }
-    for (; k < k_end; k += RSTEP) {
-        if (col_ok) {
-            typename T::Vec w = T::load(wp + (size_t)k * row_pitch);
-            T::fma(acc, w, xs[k - k_beg]);
-        }
+        for (int u = 0; u < UNROLL; ++u)
+            if (col_ok && kk + u * RSTEP < k_end) T::fma(acc, w[u], xs[kk + u * RSTEP - k_beg]);
+    };
+    for (; k < k_end; k += 2 * UNROLL * RSTEP) {
+        issue(wb, k + UNROLL * RSTEP);
+        consume(wa, k);
+        issue(wa, k + 2 * UNROLL * RSTEP);
+        consume(wb, k + UNROLL * RSTEP);
     }
 
     // rows-in-warp -> one partial per column (lanes lir, lir+LPR, ... hold the same columns)
@@ -156,8 +166,40 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     }
     __syncthreads();
 
-    // warps -> CTA partial (fixed order), then K-splits (fixed order, by the last CTA of the panel)
+    // warps -> CTA partial (fixed order), then K-splits (fixed order)
     const size_t pbase = ((size_t)batch * splits) * N;
+    if (use_cluster && splits > 1) {
+        // The K-splits of one panel form a thread-block cluster (cluster dims (1, splits, 1)): every CTA leaves its partial
+        // in its own shared memory, rank 0 sums them in rank order through distributed shared memory and writes y.  This
+        // replaces partial store + __threadfence + atomic ticket + reload (three serialized global round trips, ~3 us)
+        // by two cluster barriers -- it matters because the whole sint8 kernel should take ~10 us.
+        float* cta_part = red + WARPS * PANEL;  // PANEL floats
+        for (int c = tid; c < PANEL; c += WARPS * 32) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) s += red[(w * COLS + c % COLS) * LPR + c / COLS];
+            cta_part[c] = s;
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        if (split == 0) {
+            const uint32_t local = smem_u32(cta_part);
+            for (int c = tid; c < PANEL; c += WARPS * 32) {
+                const int gc = panel * PANEL + c;
+                float s = 0.f;
+                for (int r = 0; r < splits; ++r) {
+                    uint32_t remote;
+                    float v;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local + 4u * c), "r"(r));
+                    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+                    s += v;
+                }
+                if (gc < N) store_y(y, gc, s * out_scale, peers);
+            }
+        }
+        // nobody may exit (and release its shared memory) before rank 0 has read every partial
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        return;
+    }
     for (int c = tid; c < PANEL; c += WARPS * 32) {
         const int gc = panel * PANEL + c;
         if (gc >= N) continue;
@@ -180,8 +222,15 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     for (int c = tid; c < PANEL; c += WARPS * 32) {
         const int gc = panel * PANEL + c;
         if (gc >= N) continue;
+        // fixed summation order, but the L2 loads are issued 8 at a time (a one-at-a-time loop costs splits x ~0.4 us)
         float s = 0.f;
-        for (int sp = 0; sp < splits; ++sp) s += __ldcg(&partial[pbase + (size_t)sp * N + gc]);
+        for (int sp0 = 0; sp0 < splits; sp0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (sp0 + u < splits) ? __ldcg(&partial[pbase + (size_t)(sp0 + u) * N + gc]) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
         store_y(y, gc, s * out_scale, peers);
     }
     if (tid == 0) tickets[batch * gridDim.x + panel] = 0u;  // ready for the next launch
