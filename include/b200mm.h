@@ -160,7 +160,8 @@ B200MM_API int b200mm_launch(b200mm_ctx* ctx, b200mm_kernel* kern, const b200mm_
 B200MM_API int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* kern, const void* A, const void* B, void* C,
                                  const uint32_t grid[3]);
 /* End-to-end call with HOST buffers: H2D of A and B, launch, D2H of C, blocking.  hostA/B/C should be
- * pinned.  dA/dB/dC are caller-provided device staging buffers of matching size. */
+ * pinned.  dA/dB/dC are caller-provided device staging buffers of matching size.  For the SGEMM kernels
+ * the copies are pipelined with the compute over row panels of A / C (same tolerances as b200mm_launch). */
 B200MM_API int b200mm_mm_host(b200mm_ctx* ctx, b200mm_kernel* kern, const void* hostA, size_t bytesA, const void* hostB,
                               size_t bytesB, void* hostC, size_t bytesC, b200mm_buffer* dA, b200mm_buffer* dB,
                               b200mm_buffer* dC);

@@ -289,3 +289,29 @@ def test_launch_rejects_undersized_buffers(gpu_ctx):
     small.free()
     ok.free()
     kern.free()
+
+
+@pytest.mark.parametrize("kid_name", ["SGEMM_TC3X", "SGEMM_SIMT"])
+@pytest.mark.parametrize("size", [1024, 2048])
+def test_mm_host_end_to_end(gpu_ctx, oracle, kid_name, size):
+    """b200mm_mm_host: host A, B -> device, GEMM, C -> host (pipelined over row panels for the SGEMM kernels)."""
+    import wgpu_mm_b200 as w
+    M = N = K = size
+    A = oracle.generate_weight_data(41, M, K)
+    B = oracle.generate_weight_data(42, K, N)
+    Cm = np.full((M, N), 123.25, dtype=np.float32)
+    kern = gpu_ctx.kernel(getattr(w.KernelId, kid_name), M, N, K)
+    dA, dB, dC = gpu_ctx.buffer(M * K * 4), gpu_ctx.buffer(K * N * 4), gpu_ctx.buffer(M * N * 4)
+    for _ in range(2):  # second call reuses the cached panel kernel and B split state
+        Cm[:] = 123.25
+        gpu_ctx.mm_host(kern, A, B, Cm, dA, dB, dC)
+        assert not (Cm == 123.25).any()
+        rows = np.array([0, 1, M // 2, M - 1])
+        e, m = oracle.err_vs_f64(Cm[rows], oracle.mm_f64_rows(A, B, rows))
+        assert e / m <= REL_F64
+        assert oracle.max_abs_err(Cm[rows], oracle.mm_ref(A[rows], B)) <= GATE
+        # different B on the second call: the panel kernel must re-split it
+        B = oracle.generate_weight_data(43, K, N)
+    for b in (dA, dB, dC):
+        b.free()
+    kern.free()
