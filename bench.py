@@ -35,6 +35,12 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
+def load_traffic():
+    """DRAM bytes per launch measured by ncu (committed under profiles/); None when a kernel has no capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -170,6 +176,19 @@ def time_kernel_steps(ctx, kern, sets, steps, warmup):
     return total, per
 
 
+def time_back_to_back(ctx, kern, sets, iters, warmup):
+    """Average duration (ms) of `iters` launches issued back to back on the stream, CUDA events around the whole batch.
+    Used for the microsecond-scale GEMV kernels: they are launched with programmatic dependent launch, which an event
+    record between two launches would defeat, and a per-launch event pair has ~2 us granularity."""
+    for i in range(warmup):
+        ctx.launch(kern, *sets[i % len(sets)])
+    ctx.sync()
+    ctx.timer_begin()
+    for i in range(iters):
+        ctx.launch(kern, *sets[i % len(sets)])
+    return ctx.timer_end() / iters
+
+
 def make_sets(ctx, M, N, K, nsets, seed0, quant=False, oracle=None):
     sets = []
     for s in range(nsets):
@@ -219,8 +238,9 @@ def run_single(args):
     tc_achieved = flop / (kern_ms * 1e-3) / 1e12
     # tensor roofline: tf32 runs at half the bf16 rate and the split executes 3 MMAs per product
     tc_peak = peaks["bf16_tflops"] / 2.0 / 3.0
+    traffic = load_traffic()
     roofline = {"bound": "tensor", "achieved": tc_achieved, "peak": tc_peak, "unit": "TFLOP/s", "frac": tc_achieved / tc_peak,
-                "traffic": None, "kernel": "sgemm_tc3x_kernel", "kernel_ms": kern_ms,
+                "traffic": traffic.get("sgemm_tc3x_kernel@4096"), "kernel": "sgemm_tc3x_kernel", "kernel_ms": kern_ms,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peaks['_source']}, burst) / 2 (tf32:bf16 rate) / 3 (3xTF32 MMAs per product); "
                                f"tensor-pipe view: {3 * tc_achieved:.1f} of {peaks['bf16_tflops'] / 2:.1f} TF32 TFLOP/s"}
 
@@ -242,7 +262,7 @@ def run_single(args):
         ctx.mm_host(kern, npA, npB, npC, dA, dB, dC)  # blocking: returns when C is in host memory
     e2e_s = (time.perf_counter() - te) / e2e_steps
     e2e = {"value": flop / e2e_s / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": M * K * 4 + K * N * 4, "d2h_bytes_per_step": M * N * 4,
-           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "api": "b200mm_mm_host (pinned host A,B -> device, split + tcgen05 GEMM, C -> pinned host)"}
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "api": "b200mm_mm_host (pinned host A,B -> device, split_lo + tcgen05 GEMM, C -> pinned host; copies pipelined over 8 row panels)"}
     checksum = float(npC[:4096].astype(np.float64).sum())
     for h in (hA, hB, hC):
         w.lib().b200mm_host_free(h)
@@ -267,24 +287,24 @@ def run_single(args):
         Kv, Nv = 4096, 16384
         gsets = make_sets(ctx, 1, Nv, Kv, 4, 300)
         kg = ctx.kernel(w.KernelId.GEMV_F32, 1, Nv, Kv, w.KernelParams(tune=(args.gemv_variant, 0, 0, 0)))
-        tot, per = time_kernel_steps(ctx, kg, gsets, 40, 8)
-        ms = float(np.mean(per))
+        ms = time_back_to_back(ctx, kg, gsets, 200, 20)
+        tot = ms * 40
         gbytes = 4.0 * Kv * Nv + 4 * Kv + 4 * Nv
-        extras["gemv_f32_4096x16384"] = {"gbps": gbytes / (ms * 1e-3) / 1e9, "kernel_us": ms * 1e3, "back_to_back_us": tot / 40 * 1e3,
+        extras["gemv_f32_4096x16384"] = {"gbps": gbytes / (ms * 1e-3) / 1e9, "kernel_us": ms * 1e3, "timing": "200 back-to-back PDL launches, 4 weight sets (1 GiB) rotated",
                                          "roofline": {"bound": "hbm", "achieved": gbytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                                      "frac": gbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                                                      "frac": gbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic.get("gemv_stream_kernel<GemvF32>@4096x16384"),
                                                       "algorithmic_bytes": gbytes, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['_source']})"}}
         kg.free(); free_sets(gsets)
         # ---------------- qGEMV sint8 1x4096 * 4096x14336: 8 weight sets = 470 MB rotated (> L2) ----------------
         Kq, Nq = 4096, 14336
         qsets = make_sets(ctx, 1, Nq, Kq, 8, 500, quant=True)
         kq = ctx.kernel(w.KernelId.QGEMV_SINT8, 1, Nq, Kq, w.KernelParams(absmax=2.0, batch=1, tune=(args.gemv_variant, 0, 0, 0)))
-        tot, per = time_kernel_steps(ctx, kq, qsets, 80, 16)
-        ms = float(np.mean(per))
+        ms = time_back_to_back(ctx, kq, qsets, 400, 40)
+        tot = ms * 80
         qbytes = 1.0 * Kq * Nq + 4 * Kq + 4 * Nq
-        extras["qgemv_sint8_4096x14336"] = {"gbps": qbytes / (ms * 1e-3) / 1e9, "kernel_us": ms * 1e3, "back_to_back_us": tot / 80 * 1e3,
+        extras["qgemv_sint8_4096x14336"] = {"gbps": qbytes / (ms * 1e-3) / 1e9, "kernel_us": ms * 1e3, "timing": "400 back-to-back PDL launches, 8 weight sets (470 MB) rotated",
                                             "roofline": {"bound": "hbm", "achieved": qbytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                                         "frac": qbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                                                         "frac": qbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic.get("gemv_stream_kernel<GemvS8>@4096x14336"),
                                                          "algorithmic_bytes": qbytes, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['_source']})"}}
         kq.free(); free_sets(qsets)
 

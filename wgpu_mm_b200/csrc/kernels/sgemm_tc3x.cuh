@@ -301,6 +301,8 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    // tiles-stored counter: epilogue warps -> replicator warp (fused multi-GPU all-gather)
+    auto tiles_done_ptr = [&]() { return reinterpret_cast<volatile unsigned int*>(smem_raw + (tmem_slot + 8 - smem_u32(smem_raw))); };
     auto sA_hi = [&](int s) { return smem_base + s * STAGE_BYTES; };
     auto sA_lo = [&](int s) { return smem_base + s * STAGE_BYTES + A_BYTES; };
     auto sB_hi = [&](int s) { return smem_base + s * STAGE_BYTES + (ONE_PASS ? 1 : 2) * A_BYTES; };
@@ -327,6 +329,7 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             ptx::mbar_init(tempty_bar(s), Cfg::EPI_WARPS);  // one arrive per epilogue warp
         }
         ptx::fence_barrier_init();
+        *tiles_done_ptr() = 0;
     }
     if (warp == 2) {
         ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -428,6 +431,52 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
                     }
                 }
             }
+        } else if (warp == 3 && p.peers.world > 1) {
+            // ===================== replicator (fused all-gather) =====================
+            // The epilogue warps store a finished tile only to the LOCAL copy of C and bump tiles_done; this warp then
+            // streams the tile (L2-hot) to the same position of C on every peer over NVLink.  The NVLink back-pressure
+            // therefore never reaches the warps that drain TMEM, and the MMA pipeline keeps running (measured at 8 GPUs:
+            // stores issued by the epilogue warps themselves cost 16 % of the kernel).
+            SegIter it(p);
+            int t, c0, c1, skt;
+            unsigned int stored = 0;
+            const float* src_base = p.peers.c[p.peers.rank];
+            volatile unsigned int* tiles_done = tiles_done_ptr();
+            while (it.next(t, c0, c1, skt)) {
+                if (c0 != 0) continue;  // contributor segments do not store C
+                ++stored;
+                while (*tiles_done < stored * Cfg::EPI_WARPS) __nanosleep(200);
+                __threadfence();
+                int tm, tn;
+                tile_coords(t, tm, tn);
+                const int rows = min(BM, p.M - tm * BM);
+                const int cols4 = min(BN, p.N - tn * BN) / 4;  // float4 per tile row
+                const size_t off0 = (size_t)(tm * BM) * p.peers.ldc + p.peers.col0 + (size_t)tn * BN;
+                for (int d = 0; d < p.peers.world; ++d) {
+                    if (d == p.peers.rank) continue;
+                    float* dst_base = p.peers.c[d];
+                    for (int r = 0; r < rows; r += 4) {
+                        // 4 rows x up to 64 float4 per row: 8 independent 16-byte loads in flight per lane
+                        float4 v[4][2];
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int c4 = lane + 32 * h;
+                                if (r + rr < rows && c4 < cols4)
+                                    v[rr][h] = __ldcg(reinterpret_cast<const float4*>(src_base + off0 + (size_t)(r + rr) * p.peers.ldc) + c4);
+                            }
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int c4 = lane + 32 * h;
+                                if (r + rr < rows && c4 < cols4)
+                                    *(reinterpret_cast<float4*>(dst_base + off0 + (size_t)(r + rr) * p.peers.ldc) + c4) = v[rr][h];
+                            }
+                    }
+                }
+            }
         }
     } else {
         // ===================== epilogue: 2 warpgroups x 4 warps =====================
@@ -499,7 +548,9 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             float* stage = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw))) + (warp - 4) * 32 * Cfg::EPI_STAGE_LD;
             const int row0 = tm * BM + q * 32;
             const int col0 = tn * BN + half * COLS;
-            const int ndst = p.peers.world == 0 ? 1 : p.peers.world;
+            float* const base = p.peers.world == 0 ? p.C : p.peers.c[p.peers.rank];  // fused mode: local copy only, see replicator
+            const size_t ld = p.peers.world == 0 ? (size_t)p.ldc : p.peers.ldc;
+            const size_t coff = p.peers.world == 0 ? 0 : p.peers.col0;
 #pragma unroll  // must stay unrolled: acc[] is indexed with c and has to live in registers
             for (int c = 0; c < COLS / 32; ++c) {
                 __syncwarp();
@@ -509,23 +560,18 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
                         make_float4(acc[c * 32 + 4 * j], acc[c * 32 + 4 * j + 1], acc[c * 32 + 4 * j + 2], acc[c * 32 + 4 * j + 3]);
                 __syncwarp();
                 const int cc = col0 + c * 32 + (lane & 7) * 4;
-                float4 v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int rr = 4 * i + (lane >> 3);
-                    v[i] = *reinterpret_cast<const float4*>(stage + rr * Cfg::EPI_STAGE_LD + 4 * ((lane & 7) ^ (rr & 7)));
+                    const float4 v = *reinterpret_cast<const float4*>(stage + rr * Cfg::EPI_STAGE_LD + 4 * ((lane & 7) ^ (rr & 7)));
+                    const int r = row0 + rr;
+                    if (r < p.M && cc < p.N) *reinterpret_cast<float4*>(base + (size_t)r * ld + coff + cc) = v;
                 }
-#pragma unroll 1
-                for (int d = 0; d < ndst; ++d) {
-                    float* base = p.peers.world == 0 ? p.C : p.peers.c[d];
-                    const size_t ld = p.peers.world == 0 ? (size_t)p.ldc : p.peers.ldc;
-                    const size_t coff = p.peers.world == 0 ? 0 : p.peers.col0;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = row0 + 4 * i + (lane >> 3);
-                        if (r < p.M && cc < p.N) *reinterpret_cast<float4*>(base + (size_t)r * ld + coff + cc) = v[i];
-                    }
-                }
+            }
+            if (p.peers.world > 1) {
+                __threadfence();  // the tile is in (local) global memory before the replicator is told
+                __syncwarp();
+                if (lane == 0) atomicAdd(const_cast<unsigned int*>(tiles_done_ptr()), 1u);
             }
         }
     }
