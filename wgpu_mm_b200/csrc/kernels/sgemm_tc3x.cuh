@@ -1,33 +1,33 @@
 // FP32-accurate SGEMM on the 5th-generation tensor cores: TMA -> shared memory -> tcgen05.mma
 // (kind::tf32) -> TMEM accumulators -> tcgen05.ld epilogue, with the 3xTF32 split
 //
-//     x = hi + lo,  hi = tf32(x) (round to nearest),  lo = tf32(x - hi)
+//     x = hi + lo,  hi = trunc_tf32(x) -- applied by the tensor core itself to the raw operand --, lo = tf32(x - hi)
 //     A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi        (the lo*lo term is below fp32 resolution)
 //
 // This is north_star's main SGEMM kernel; it replaces the register-tiled WGSL shaders
 // (shaders/gemm/gemm_5.wgsl:15-86 and the orphan bram/gemm3 kernels) for C = A*B with
 // A (M x K), B (K x N), C (M x N) row-major f32 (src/harness.rs:17-28 fixes the layout).
 //
-//     x = hi + lo,  hi = trunc_tf32(x) -- applied by the tensor core itself to the raw operand --, lo = tf32(x - hi)
-//
 // Two kernels per GEMM:
 //   1. split_lo_kernel     elementwise pass, HBM-bound: reads A and B once, writes A_lo and B_lo
 //                          (kind::tf32 ignores the low 13 mantissa bits of its 32-bit operands: the raw operand
 //                          is consumed as hi, lo must be materialised);
-//   2. sgemm_tc3x_kernel   persistent, warp-specialised:
-//        warp 0    TMA producer: per k-block loads A_hi/A_lo (128 x 32, K-major, SWIZZLE_128B) and
-//                  B_hi/B_lo (32 x BN, N-major: B is K x N row-major, so it is consumed as an MN-major
+//   2. sgemm_tc3x_kernel   persistent, warp-specialised, 384 threads, one CTA per SM, tile 128 x BN x BK:
+//        warp 0    TMA producer: per k-block loads A / A_lo (128 x BK, K-major, SWIZZLE_128B or _64B) and
+//                  B / B_lo (BK x BN, N-major: B is K x N row-major, so it is consumed as an MN-major
 //                  operand straight from its natural layout -- no transpose anywhere; a 3-D tensor map
 //                  (n%32, k, n/32) with SWIZZLE_128B_ATOM_32B lands the canonical MN-major atoms)
 //        warp 1    MMA issuer: one elected thread issues 3 x (BK/8) tcgen05.mma per k-block into a
 //                  128 x BN fp32 accumulator in TMEM; tcgen05.commit releases the smem stage
 //        warp 2    TMEM allocator
-//        warps 4-11 epilogue (two warpgroups, one per column half): after every CHAIN k-blocks tcgen05.ld the
-//                  finished chain from TMEM and fold it into fp32 register accumulators with round-to-nearest
-//                  adds (the tensor core's own accumulation truncates); at the end of the tile float4 stores
-//                  to C (and, for the N-sharded multi-GPU path, to the same tile of C on every peer GPU)
+//        warp 3    replicator (multi-GPU fused all-gather only): streams finished tiles to the peers over NVLink
+//        warps 4-11 epilogue (two warpgroups, one per column half): after every 256 k tcgen05.ld the finished
+//                  chain from TMEM and fold it into fp32 register accumulators with round-to-nearest adds (the
+//                  tensor core's own accumulation truncates); at the end of the tile transpose through
+//                  swizzled shared memory and store 128-byte row segments to C
 //      Two chain accumulators ping-pong in TMEM (2 x BN columns), so folding chain i overlaps the MMAs of
-//      chain i+1, across tile boundaries as well.
+//      chain i+1, across tile boundaries as well.  Tiles are scheduled in full waves plus a stream-K tail
+//      (Tc3xArgs) and rasterised in bands of 16 tile rows.
 //
 // Roofline: tensor pipe.  Algorithmic work 2*M*N*K flop; the tensor pipe executes 3x that in TF32.
 #pragma once
