@@ -315,3 +315,37 @@ def test_mm_host_end_to_end(gpu_ctx, oracle, kid_name, size):
     for b in (dA, dB, dC):
         b.free()
     kern.free()
+
+
+@pytest.mark.parametrize("quant", [False, True])
+def test_gemv_dependent_chain_with_pdl(gpu_ctx, oracle, quant):
+    """x_{i+1} = y_i through the same square weight matrix, 24 launches back to back.  The GEMV kernels are launched with
+    programmatic dependent launch and prefetch their weights BEFORE griddepcontrol.wait; anything that depends on the
+    previous kernel (x, partials, y) must only be touched after it -- a violation shows up as a wrong chain result."""
+    import wgpu_mm_b200 as w
+    n = 1024
+    x0 = oracle.generate_weight_data(51, 1, n)
+    W = oracle.generate_weight_data(52, n, n) * np.float32(0.35)  # keeps the iterates O(0.1)
+    if quant:
+        words, absmax = oracle.sint8_quantize(W, n, n)
+        dW = gpu_ctx.buffer_from(words)
+        Wd = oracle.sint8_dequantize(words, absmax, n, n).astype(np.float64)
+        kern = gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 1, n, n, w.KernelParams(absmax=absmax, batch=1))
+    else:
+        dW = gpu_ctx.buffer_from(W)
+        Wd = W.astype(np.float64)
+        kern = gpu_ctx.kernel(w.KernelId.GEMV_F32, 1, n, n)
+    bufs = [gpu_ctx.buffer_from(x0), gpu_ctx.buffer(n * 4)]
+    steps = 24
+    for i in range(steps):
+        gpu_ctx.launch(kern, bufs[i % 2], dW, bufs[(i + 1) % 2])
+    got = bufs[steps % 2].read(np.float32).astype(np.float64)
+    ref = x0.astype(np.float64).reshape(-1)
+    for i in range(steps):
+        ref = ref @ Wd
+    scale = np.abs(ref).max()
+    assert scale > 1e-12
+    assert np.abs(got - ref).max() / scale < 1e-4, "dependent GEMV chain diverged: PDL ordering violated?"
+    for b in bufs + [dW]:
+        b.free()
+    kern.free()
