@@ -104,6 +104,8 @@ def cpu_mm_ref_sample(M, N, K, target_s=12.0, reps=1):
     workload sized for ~target_s seconds.  Returns (tflops, rows, seconds, cores)."""
     import oracle
     oracle.build()
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can get
+    oracle.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     cores = oracle.num_threads()
     B = oracle.generate_weight_data(2, K, N)
     probe_rows = max(8, min(M, cores * 2))
@@ -127,6 +129,7 @@ def run_reference(args):
     M, N, K = (4096, 4096, 4096) if N_gpus == 1 else (16384, 16384, 16384)
     import oracle
     oracle.build()
+    oracle.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     cores = oracle.num_threads()
     # each step = one bounded sample; size it so warmup+steps finish within a few minutes
     budget_s = 120.0 / max(1, args.steps + args.warmup)

@@ -189,6 +189,13 @@ B200MM_API int b200mm_ipc_import(b200mm_ctx* ctx, const void* handle64, size_t b
  * y vectors (ldc is ignored) and col_offset the first output of this rank's slice. */
 B200MM_API int b200mm_kernel_set_peers(b200mm_kernel* kern, int rank, int world, void* const* peer_c, size_t ldc,
                                        size_t col_offset);
+/* Stream-ordered barrier across the ranks of one box without a collective library: `local_flags` is a
+ * library-allocated, zero-initialised buffer of >= world u32 on every rank, `peer_flags[r]` its mapping on
+ * rank r (b200mm_ipc_import; own entry = local).  The kernel stores a per-call epoch into slot `rank` of every
+ * peer's flags and spins until all `world` local slots carry it: everything enqueued on the ctx stream before
+ * the call on ANY rank (e.g. the peer stores of a fused GEMM) has completed when it returns on the stream.
+ * Every rank must call it the same number of times. */
+B200MM_API int b200mm_peer_barrier(b200mm_ctx* ctx, b200mm_buffer* local_flags, void* const* peer_flags, int rank, int world);
 /* After an NCCL all-gather of column panels (layout [world][M][N/world]) interleave them into
  * row-major C (M x N).  `gathered` and `C` are device pointers. */
 B200MM_API int b200mm_unshard_columns(b200mm_ctx* ctx, const void* gathered, void* C, size_t M, size_t N, int world);

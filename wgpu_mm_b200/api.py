@@ -131,6 +131,10 @@ class Context:
     def flush_l2(self):
         check(lib().b200mm_flush_l2(self._h), self._h)
 
+    def peer_barrier(self, local_flags: "Buffer", peer_ptrs: Sequence[int], rank: int, world: int):
+        arr = (C.c_void_p * world)(*[C.c_void_p(p) for p in peer_ptrs])
+        check(lib().b200mm_peer_barrier(self._h, local_flags.handle, arr, rank, world), self._h)
+
     def unshard_columns(self, gathered_ptr: int, c_ptr: int, M: int, N: int, world: int):
         check(lib().b200mm_unshard_columns(self._h, C.c_void_p(gathered_ptr), C.c_void_p(c_ptr), M, N, world), self._h)
 

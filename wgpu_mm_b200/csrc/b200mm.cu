@@ -47,6 +47,7 @@ struct b200mm_buffer {
     size_t bytes = 0;
     bool owned = false;
     bool ipc = false;
+    unsigned int barrier_epoch = 0;  // b200mm_peer_barrier call count when used as a flags buffer
 };
 
 struct b200mm_kernel {
@@ -1175,6 +1176,23 @@ extern "C" int b200mm_ipc_import(b200mm_ctx* ctx, const void* handle64, size_t b
     b->bytes = bytes;
     b->ipc = true;
     *out = b;
+    return B200MM_OK;
+}
+
+extern "C" int b200mm_peer_barrier(b200mm_ctx* ctx, b200mm_buffer* local_flags, void* const* peer_flags, int rank, int world) {
+    if (!ctx || !local_flags || !peer_flags) return fail(ctx, B200MM_ERR_INVALID, "peer_barrier: NULL argument");
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(ctx, B200MM_ERR_INVALID, "peer_barrier: bad rank/world");
+    if (local_flags->bytes < (size_t)world * 4) return fail(ctx, B200MM_ERR_INVALID, "peer_barrier: flags buffer too small");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    PeerFlags pf{};
+    for (int i = 0; i < world; ++i) {
+        if (!peer_flags[i]) return fail(ctx, B200MM_ERR_INVALID, "peer_barrier: peer %d is NULL", i);
+        pf.f[i] = (unsigned int*)peer_flags[i];
+    }
+    const unsigned int epoch = ++local_flags->barrier_epoch;
+    peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(pf, (unsigned int*)local_flags->ptr, rank, world, epoch);
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
     return B200MM_OK;
 }
 

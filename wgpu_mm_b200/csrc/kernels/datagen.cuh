@@ -50,6 +50,27 @@ __global__ void unshard_columns_kernel(const float4* __restrict__ gathered, floa
     }
 }
 
+// Cross-GPU barrier over peer-mapped flag words (b200mm_peer_barrier).  Thread d publishes this rank's arrival to
+// rank d (system-scope release: everything this GPU wrote before, including stores to peers, is visible first), then
+// waits for rank d's arrival in the local flags.
+struct PeerFlags {
+    unsigned int* f[8];
+};
+__global__ void peer_barrier_kernel(PeerFlags peers, unsigned int* local, int rank, int world, unsigned int epoch) {
+    const int d = threadIdx.x;
+    if (d >= world) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.f[d] + rank), "r"(epoch) : "memory");
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    unsigned int seen;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(local + d) : "memory");
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 10000000000ull) __trap();  // 10 s: a peer never arrived -- fail loudly instead of hanging the GPU
+    } while ((int)(seen - epoch) < 0);
+}
+
 // > L2-sized write used by b200mm_flush_l2.
 __global__ void flush_kernel(float4* __restrict__ p, size_t n4, float v) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
