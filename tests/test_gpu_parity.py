@@ -349,3 +349,37 @@ def test_gemv_dependent_chain_with_pdl(gpu_ctx, oracle, quant):
     for b in bufs + [dW]:
         b.free()
     kern.free()
+
+
+@pytest.mark.parametrize("m", [2, 4, 8])
+@pytest.mark.parametrize("kn", [(512, 1024), (4096, 4096), (1000, 260)])
+def test_gemv_f32_skinny_m(gpu_ctx, oracle, m, kn):
+    """Skinny GEMM: M rows of x share one pass over W; semantics = mm_ref with M rows."""
+    import wgpu_mm_b200 as w
+    K, N = kn
+    X = oracle.generate_weight_data(61, m, K)
+    W = oracle.generate_weight_data(62, K, N)
+    got = _run(gpu_ctx, w.KernelId.GEMV_F32, X, W, m, N, K)
+    _check(oracle, got, X, W)
+
+
+@pytest.mark.parametrize("m", [2, 4])
+def test_qgemv_sint8_skinny_m(gpu_ctx, oracle, m):
+    import wgpu_mm_b200 as w
+    K, N = 1024, 2048
+    X = oracle.generate_weight_data(63, m, K)
+    W = oracle.generate_weight_data(64, K, N)
+    words, _ = oracle.sint8_quantize(W, K, N)
+    got = _run(gpu_ctx, w.KernelId.QGEMV_SINT8, X, words, m, N, K, w.KernelParams(absmax=2.0, batch=1), b_dtype=np.uint32)
+    ref = oracle.qgemv_ref(X, words, m, N, K, 2.0)
+    assert oracle.max_abs_err(got, ref) <= GATE
+    e, mx = oracle.err_vs_f64(got, oracle.qgemv_f64(X, words, m, N, K, 2.0))
+    assert e / mx <= REL_F64
+
+
+def test_gemv_rejects_unsupported_m(gpu_ctx):
+    import wgpu_mm_b200 as w
+    with pytest.raises(w.B200mmError):
+        gpu_ctx.kernel(w.KernelId.GEMV_F32, 3, 1024, 1024)
+    with pytest.raises(w.B200mmError):
+        gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 8, 1024, 1024, w.KernelParams(absmax=2.0))

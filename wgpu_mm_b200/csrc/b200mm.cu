@@ -405,7 +405,20 @@ using Tc256x1 = Tc3xCfg<256, 4, true, 32>;
 template <class T>
 static void gemv_pick(int variant, void (**fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float,
                                                size_t, size_t, size_t, PeerStore, int),
-                      int* warps, int* lpr) {
+                      int* warps, int* lpr, int mrows = 1) {
+    if (mrows > 1) {
+        // skinny GEMM: only the default geometry of each weight type is instantiated for M = 2, 4, 8
+        if constexpr (T::COLS == 4) {
+            *fn = mrows == 2 ? gemv_stream_kernel<T, 4, 4, 32, 2> : mrows == 4 ? gemv_stream_kernel<T, 4, 4, 32, 4> : gemv_stream_kernel<T, 4, 4, 32, 8>;
+            *warps = 4;
+            *lpr = 32;
+        } else {
+            *fn = mrows == 2 ? gemv_stream_kernel<T, 8, 4, 16, 2> : gemv_stream_kernel<T, 8, 4, 16, 4>;
+            *warps = 8;
+            *lpr = 16;
+        }
+        return;
+    }
     if (variant == 1) {
         *fn = gemv_stream_kernel<T, 8, 8, 16>;
         *warps = 8;
@@ -631,7 +644,12 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
 static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     const size_t M = k->M, N = k->N, K = k->K;
     const int cols = quant ? 16 : 4;
-    if (M != 1) return fail(ctx, B200MM_ERR_INVALID, "%s needs M == 1 (use batch for several vectors)", b200mm_kernel_name(k->id));
+    const int max_m = quant ? 4 : 8;
+    if (M != 1 && M != 2 && M != 4 && !(M == 8 && !quant))
+        return fail(ctx, B200MM_ERR_INVALID, "%s takes M in {1, 2, 4%s} rows of x (skinny GEMM); use an SGEMM kernel for larger M", b200mm_kernel_name(k->id),
+                    quant ? "" : ", 8");
+    (void)max_m;
+    const int mrows = (int)M;
     if (N % cols || K % 4)
         return fail(ctx, B200MM_ERR_INVALID, "%s needs N%%%d==0 and K%%4==0", b200mm_kernel_name(k->id), cols);
     if (N > INT32_MAX || K > INT32_MAX) return fail(ctx, B200MM_ERR_INVALID, "shape too large");
@@ -666,9 +684,9 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t, PeerStore, int);
     int warps, lpr;
     if (quant)
-        gemv_pick<GemvS8>(k->gemv_variant, &fn, &warps, &lpr);
+        gemv_pick<GemvS8>(k->gemv_variant, &fn, &warps, &lpr, mrows);
     else
-        gemv_pick<GemvF32>(k->gemv_variant, &fn, &warps, &lpr);
+        gemv_pick<GemvF32>(k->gemv_variant, &fn, &warps, &lpr, mrows);
     const int panel = lpr * cols;
     const unsigned batch = k->prm.batch ? k->prm.batch : 1;
     k->panels = (int)ceil_div(N, panel);
@@ -688,7 +706,8 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
         splits = (int)std::min<size_t>(splits, std::max<size_t>(1, K / 32));
     }
     // K-splits of a panel are reduced inside a thread-block cluster (<= 8 CTAs, portable size) unless tune[3] == 1
-    k->gemv_cluster = (k->prm.tune[3] != 1);
+    k->gemv_cluster = (k->prm.tune[3] != 1) || mrows > 1;  // the ticket path exists for M == 1 only
+    if (mrows > 1 && splits > 8) splits = 8;
     if (k->gemv_cluster && splits > 8) {
         if (k->prm.tune[1] > 0)
             k->gemv_cluster = false;  // an explicit split count above 8 keeps the ticket path
@@ -703,7 +722,7 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     k->rows_per_split = (int)rps;
     k->grid = dim3(k->panels, splits, batch);
     k->block = dim3(warps * 32, 1, 1);
-    k->smem = (rps + (size_t)warps * panel + panel) * sizeof(float);
+    k->smem = ((size_t)mrows * rps + (size_t)warps * mrows * panel + (size_t)mrows * panel) * sizeof(float);
     if (k->smem > 200 * 1024) return fail(ctx, B200MM_ERR_INVALID, "gemv: K-split too long for shared memory");
     CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(k->smem, 48 * 1024)));
     if (splits > 1 && !k->gemv_cluster) {
@@ -985,12 +1004,12 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
             void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t, PeerStore, int);
             int warps, lpr;
             if (quant)
-                gemv_pick<GemvS8>(k->gemv_variant, &fn, &warps, &lpr);
+                gemv_pick<GemvS8>(k->gemv_variant, &fn, &warps, &lpr, (int)k->M);
             else
-                gemv_pick<GemvF32>(k->gemv_variant, &fn, &warps, &lpr);
+                gemv_pick<GemvF32>(k->gemv_variant, &fn, &warps, &lpr, (int)k->M);
             const float scale = quant ? k->prm.absmax / 127.0f : 1.0f;
             const size_t wstride = quant ? (size_t)K * N : (size_t)K * N * 4;
-            if (k->peers.world && (k->prm.batch > 1)) return fail(ctx, B200MM_ERR_INVALID, "peer stores are not supported for batched GEMV");
+            if (k->peers.world && (k->prm.batch > 1 || k->M > 1)) return fail(ctx, B200MM_ERR_INVALID, "peer stores are not supported for batched / multi-row GEMV");
             // launched with programmatic stream serialization (PDL): see the griddepcontrol comments in gemv.cuh
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = k->grid;
@@ -1011,7 +1030,7 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
                 cfg.numAttrs = 2;
             }
             CU_TRY(ctx, cudaLaunchKernelEx(&cfg, fn, Af, (const void*)B, Cf, k->partial, k->tickets, (int)K, (int)N, k->rows_per_split, scale,
-                                           (size_t)K, wstride, (size_t)N, k->peers, cluster ? 1 : 0));
+                                           (size_t)k->M * K, wstride, (size_t)k->M * N, k->peers, cluster ? 1 : 0));
             break;
         }
         default:

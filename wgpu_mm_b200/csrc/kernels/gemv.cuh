@@ -88,7 +88,8 @@ __device__ __forceinline__ void store_y(float* y, int gc, float v, const PeerSto
 //   LPR   lanes per row segment (32 or 16): a warp reads 32/LPR rows per load instruction
 //   panel = LPR * COLS columns;   rows of a split are dealt round-robin to (warp, row-in-warp) slots.
 // partial: [batch][splits][N] floats, tickets: [batch][panels] u32 (zeroed once; self-resetting).
-template <class T, int WARPS, int UNROLL, int LPR>
+// MROWS > 1: skinny GEMM -- MROWS rows of x (row-major MROWS x K) share one pass over W; y is MROWS x N.
+template <class T, int WARPS, int UNROLL, int LPR, int MROWS = 1>
 __global__ void __launch_bounds__(WARPS * 32)
 gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, float* __restrict__ y,
                    float* __restrict__ partial, unsigned int* __restrict__ tickets, int K, int N, int rows_per_split,
@@ -99,8 +100,8 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     constexpr int RSTEP = WARPS * RPW;   // rows per CTA per load
     constexpr int PANEL = LPR * COLS;
     extern __shared__ __align__(16) float sm[];
-    float* xs = sm;                         // rows_per_split floats
-    float* red = sm + rows_per_split;       // WARPS * PANEL floats
+    float* xs = sm;                                 // MROWS * rows_per_split floats
+    float* red = sm + MROWS * rows_per_split;       // WARPS * MROWS * PANEL floats
     __shared__ unsigned int s_ticket;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -135,17 +136,24 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     issue(wa, k);
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    for (int i = tid; i < rows_per_split; i += WARPS * 32) xs[i] = (k_beg + i < k_end) ? x[k_beg + i] : 0.f;
+#pragma unroll
+    for (int m = 0; m < MROWS; ++m)
+        for (int i = tid; i < rows_per_split; i += WARPS * 32) xs[m * rows_per_split + i] = (k_beg + i < k_end) ? x[(size_t)m * K + k_beg + i] : 0.f;
     __syncthreads();
 
-    float acc[COLS];
+    float acc[MROWS][COLS];
 #pragma unroll
-    for (int j = 0; j < COLS; ++j) acc[j] = 0.f;
+    for (int m = 0; m < MROWS; ++m)
+#pragma unroll
+        for (int j = 0; j < COLS; ++j) acc[m][j] = 0.f;
 
     auto consume = [&](const typename T::Vec (&w)[UNROLL], int kk) {
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
-            if (col_ok && kk + u * RSTEP < k_end) T::fma(acc, w[u], xs[kk + u * RSTEP - k_beg]);
+            if (col_ok && kk + u * RSTEP < k_end) {
+#pragma unroll
+                for (int m = 0; m < MROWS; ++m) T::fma(acc[m], w[u], xs[m * rows_per_split + kk + u * RSTEP - k_beg]);
+            }
     };
     for (; k < k_end; k += 2 * UNROLL * RSTEP) {
         issue(wb, k + UNROLL * RSTEP);
@@ -158,11 +166,15 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
 #pragma unroll
     for (int off = LPR; off < 32; off <<= 1) {
 #pragma unroll
-        for (int j = 0; j < COLS; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+        for (int m = 0; m < MROWS; ++m)
+#pragma unroll
+            for (int j = 0; j < COLS; ++j) acc[m][j] += __shfl_xor_sync(0xffffffffu, acc[m][j], off);
     }
     if (riw == 0) {
 #pragma unroll
-        for (int j = 0; j < COLS; ++j) red[(warp * COLS + j) * LPR + lir] = acc[j];  // [warp][j][lane]: conflict-free stores
+        for (int m = 0; m < MROWS; ++m)
+#pragma unroll
+            for (int j = 0; j < COLS; ++j) red[((warp * MROWS + m) * COLS + j) * LPR + lir] = acc[m][j];  // [warp][m][j][lane]: conflict-free
     }
     __syncthreads();
 
@@ -173,18 +185,19 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
         // in its own shared memory, rank 0 sums them in rank order through distributed shared memory and writes y.  This
         // replaces partial store + __threadfence + atomic ticket + reload (three serialized global round trips, ~3 us)
         // by two cluster barriers -- it matters because the whole sint8 kernel should take ~10 us.
-        float* cta_part = red + WARPS * PANEL;  // PANEL floats
-        for (int c = tid; c < PANEL; c += WARPS * 32) {
+        float* cta_part = red + WARPS * MROWS * PANEL;  // MROWS * PANEL floats
+        for (int c = tid; c < MROWS * PANEL; c += WARPS * 32) {
+            const int m = c / PANEL, cc = c % PANEL;
             float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < WARPS; ++w) s += red[(w * COLS + c % COLS) * LPR + c / COLS];
+            for (int w = 0; w < WARPS; ++w) s += red[((w * MROWS + m) * COLS + cc % COLS) * LPR + cc / COLS];
             cta_part[c] = s;
         }
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
         if (split == 0) {
             const uint32_t local = smem_u32(cta_part);
-            for (int c = tid; c < PANEL; c += WARPS * 32) {
-                const int gc = panel * PANEL + c;
+            for (int c = tid; c < MROWS * PANEL; c += WARPS * 32) {
+                const int m = c / PANEL, gc = panel * PANEL + c % PANEL;
                 float s = 0.f;
                 for (int r = 0; r < splits; ++r) {
                     uint32_t remote;
@@ -193,23 +206,24 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
                     asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
                     s += v;
                 }
-                if (gc < N) store_y(y, gc, s * out_scale, peers);
+                if (gc < N) store_y(y + (size_t)m * N, gc, s * out_scale, peers);
             }
         }
         // nobody may exit (and release its shared memory) before rank 0 has read every partial
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
         return;
     }
-    for (int c = tid; c < PANEL; c += WARPS * 32) {
-        const int gc = panel * PANEL + c;
+    for (int c = tid; c < MROWS * PANEL; c += WARPS * 32) {
+        const int m = c / PANEL, cc = c % PANEL;
+        const int gc = panel * PANEL + cc;
         if (gc >= N) continue;
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) s += red[(w * COLS + c % COLS) * LPR + c / COLS];
+        for (int w = 0; w < WARPS; ++w) s += red[((w * MROWS + m) * COLS + cc % COLS) * LPR + cc / COLS];
         if (splits == 1)
-            store_y(y, gc, s * out_scale, peers);
+            store_y(y + (size_t)m * N, gc, s * out_scale, peers);
         else
-            partial[pbase + (size_t)split * N + gc] = s;
+            partial[pbase + (size_t)split * N + gc] = s;  // ticket path: MROWS == 1 only (the host never selects it otherwise)
     }
     if (splits == 1) return;
 
