@@ -20,7 +20,6 @@
 #include "kernels/sgemm_tc3x.cuh"
 #include "kernels/wgsl_ports.cuh"
 #include "kernels/tc_probe.cuh"
-#include "kernels/qgemv_tma.cuh"
 
 using namespace b200mm;
 
@@ -73,9 +72,6 @@ struct b200mm_kernel {
     // gemv
     int splits = 1, rows_per_split = 0, panels = 0, gemv_variant = 0;
     bool gemv_cluster = false;
-    bool qgemv_tma = false;      // TMA-staged sint8 kernel (batch 1)
-    CUtensorMap tmW{};
-    const void* tmW_src = nullptr;
     float* partial = nullptr;
     unsigned int* tickets = nullptr;
     // simt schedule: launch 1 = simt_tiles1 whole tiles, launch 2 = simt_tiles2 tiles x simt.split K-parts
@@ -654,32 +650,6 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
         return fail(ctx, B200MM_ERR_INVALID, "%s needs N%%%d==0 and K%%4==0", b200mm_kernel_name(k->id), cols);
     if (N > INT32_MAX || K > INT32_MAX) return fail(ctx, B200MM_ERR_INVALID, "shape too large");
     // tune[0]: 0 = default for the weight type (measured on B200, tools/sweep_gemv.py), 100 = variant 0, else the variant id
-    // sint8, batch 1, tune[0] = 200: TMA-staged kernel (kernels/qgemv_tma.cuh).  Measured equal to the register-streaming
-    // default at BASELINE config 3 (15.8 vs 15.6 us): the shape is bound by ~7 us of per-launch fixed cost plus the
-    // dequant issue time, not by bytes in flight, so the simpler kernel stays the default.
-    if (quant && (k->prm.batch <= 1) && k->prm.tune[0] == 200 && ctx->prop.major >= 9 && N % 16 == 0) {
-        using Q = QgemvTmaCfg;
-        k->qgemv_tma = true;
-        k->panels = (int)ceil_div(N, Q::PANEL);
-        int splits = (int)k->prm.tune[1];
-        if (splits <= 0) {
-            // one resident wave: 3 CTAs of 288 threads and ~70 KB of shared memory fit per SM
-            splits = (int)(((size_t)ctx->prop.multiProcessorCount * 3) / (size_t)k->panels);
-            splits = std::max(1, std::min(splits, 8));
-        }
-        splits = std::max(1, std::min(splits, 8));
-        size_t rps = ceil_div(K, (size_t)splits);
-        rps = ceil_div(rps, Q::STAGE_ROWS) * Q::STAGE_ROWS;
-        splits = (int)ceil_div(K, rps);
-        k->splits = splits;
-        k->rows_per_split = (int)rps;
-        k->grid = dim3(k->panels, splits, 1);
-        k->block = dim3(Q::THREADS, 1, 1);
-        static_assert((Q::CONSUMER_WARPS + 1) * Q::PANEL * 4 <= Q::STAGES * Q::STAGE_BYTES, "reduction scratch aliases the ring");
-        k->smem = 128 + Q::STAGES * Q::STAGE_BYTES + 16 * Q::STAGES + rps * sizeof(float);
-        CU_TRY(ctx, cudaFuncSetAttribute(qgemv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
-        return B200MM_OK;
-    }
     k->gemv_variant = k->prm.tune[0] == 0 ? (quant ? 4 : 5) : (k->prm.tune[0] == 100 ? 0 : (int)k->prm.tune[0]);
     void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t, PeerStore, int);
     int warps, lpr;
@@ -966,41 +936,6 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
         case B200MM_K_GEMV_F32:
         case B200MM_K_QGEMV_SINT8: {
             const bool quant = k->id == B200MM_K_QGEMV_SINT8;
-            if (k->qgemv_tma) {
-                if (k->tmW_src != B) {
-                    PFN_encodeTiled enc = get_encode_tiled();
-                    if (!enc) return fail(ctx, B200MM_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-                    if ((uintptr_t)B & 15) return fail(ctx, B200MM_ERR_INVALID, "qgemv_sint8 needs a 16-byte aligned weight buffer");
-                    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)K};
-                    cuuint64_t strides[1] = {(cuuint64_t)N};
-                    cuuint32_t box[2] = {QgemvTmaCfg::PANEL, QgemvTmaCfg::STAGE_ROWS};
-                    cuuint32_t estr[2] = {1, 1};
-                    CUresult r = enc(&k->tmW, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(B), dims, strides, box, estr,
-                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                    if (r != CUDA_SUCCESS) return fail(ctx, B200MM_ERR_CUDA, "cuTensorMapEncodeTiled(qgemv weights) failed: %d", (int)r);
-                    k->tmW_src = B;
-                }
-                cudaLaunchConfig_t cfg{};
-                cfg.gridDim = k->grid;
-                cfg.blockDim = k->block;
-                cfg.dynamicSmemBytes = k->smem;
-                cfg.stream = s;
-                cudaLaunchAttribute attr[2];
-                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                attr[0].val.programmaticStreamSerializationAllowed = (k->prm.tune[2] == 1) ? 0 : 1;
-                cfg.attrs = attr;
-                cfg.numAttrs = 1;
-                if (k->splits > 1) {
-                    attr[1].id = cudaLaunchAttributeClusterDimension;
-                    attr[1].val.clusterDim.x = 1;
-                    attr[1].val.clusterDim.y = (unsigned)k->splits;
-                    attr[1].val.clusterDim.z = 1;
-                    cfg.numAttrs = 2;
-                }
-                CU_TRY(ctx, cudaLaunchKernelEx(&cfg, qgemv_tma_kernel, k->tmW, Af, Cf, (int)K, (int)N, k->rows_per_split, k->prm.absmax / 127.0f, k->peers));
-                break;
-            }
             void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t, PeerStore, int);
             int warps, lpr;
             if (quant)

@@ -452,22 +452,24 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
                 const int rows = min(BM, p.M - tm * BM);
                 const int cols4 = min(BN, p.N - tn * BN) / 4;  // float4 per tile row
                 const size_t off0 = (size_t)(tm * BM) * p.peers.ldc + p.peers.col0 + (size_t)tn * BN;
-                for (int d = 0; d < p.peers.world; ++d) {
-                    if (d == p.peers.rank) continue;
-                    float* dst_base = p.peers.c[d];
-                    for (int r = 0; r < rows; r += 4) {
-                        // 4 rows x up to 64 float4 per row: 8 independent 16-byte loads in flight per lane
-                        float4 v[4][2];
+                for (int r = 0; r < rows; r += 8) {
+                    // 8 rows x up to 64 float4 per row are read ONCE (16 independent 16-byte loads in flight per lane) and
+                    // fanned out from registers to every peer
+                    float4 v[8][2];
 #pragma unroll
-                        for (int rr = 0; rr < 4; ++rr)
+                    for (int rr = 0; rr < 8; ++rr)
 #pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const int c4 = lane + 32 * h;
-                                if (r + rr < rows && c4 < cols4)
-                                    v[rr][h] = __ldcg(reinterpret_cast<const float4*>(src_base + off0 + (size_t)(r + rr) * p.peers.ldc) + c4);
-                            }
+                        for (int h = 0; h < 2; ++h) {
+                            const int c4 = lane + 32 * h;
+                            if (r + rr < rows && c4 < cols4)
+                                v[rr][h] = __ldcg(reinterpret_cast<const float4*>(src_base + off0 + (size_t)(r + rr) * p.peers.ldc) + c4);
+                        }
+#pragma unroll 1
+                    for (int d = 0; d < p.peers.world; ++d) {
+                        if (d == p.peers.rank) continue;
+                        float* dst_base = p.peers.c[d];
 #pragma unroll
-                        for (int rr = 0; rr < 4; ++rr)
+                        for (int rr = 0; rr < 8; ++rr)
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
                                 const int c4 = lane + 32 * h;
