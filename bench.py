@@ -322,12 +322,36 @@ def run_single(args):
                                            "note": "same kernel and schedule as the N-sharded runs; sustained clocks (power cap) apply"}
         kb.free(); free_sets(bsets)
 
+    if not args.no_extras:
+        # ---------------- BASELINE configs[0]: the reference's own test shape (1024^3) through the host harness ----------------
+        # verify (max-abs-err <= 1e-3 vs mm_ref) -> 8 warm-up -> 10 timed launches + read-back, exactly src/harness.rs:170-248;
+        # "gflops" is the reference-style number (wall clock incl. the D2H of C), "kernel_gflops" the CUDA-event one
+        from wgpu_mm_b200 import harness as hz
+        h = {}
+        for entry in ("gemm_wonnx", "gemm_5", "sgemm_simt", "sgemm_tc3x"):
+            r = hz.test_harness(None, entry, (1024, 1024, 1024), False)
+            h[entry] = {"reference_style_gflops": r.gflops, "kernel_gflops": r.kernel_gflops, "max_abs_err": r.max_abs_err,
+                        "max_rel_err_f64": r.max_rel_err_f64}
+        r = hz.test_harness(None, "qgemv_1", (1, 1024, 1024), True)
+        h["qgemv_1"] = {"kernel_gbps": r.kernel_gbps, "max_abs_err": r.max_abs_err}
+        extras["harness_1024_reference_shapes"] = h
+
     # ---------------- CPU baseline (reported, not the target) ----------------
     cpu = None
     if not args.no_cpu:
         tf, rows, dt, cores = cpu_mm_ref_sample(M, N, K, target_s=12.0)
         cpu = {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port",
                "sample": f"mm_ref (src/harness.rs:17-28 restated, OpenMP) on rows 0..{rows - 1} of the 4096^3 product, {dt:.1f} s"}
+        # the gemm.wgsl (+gemm_macro.wgsl) per-invocation restatement at 1024^3 on all host cores --
+        # the stand-in for "the WGSL path on a software Vulkan adapter", which cannot run here (no wgpu / lavapipe)
+        import oracle
+        A1 = oracle.generate_weight_data(1, 1024, 1024); B1 = oracle.generate_weight_data(2, 1024, 1024)
+        oracle.wgsl_gemm("gemm_wonnx", A1, B1)
+        t = time.perf_counter()
+        for _ in range(5):
+            oracle.wgsl_gemm("gemm_wonnx", A1, B1)
+        dtw = (time.perf_counter() - t) / 5
+        cpu["gemm_wgsl_restatement_1024_gflops"] = 2.0 * 1024 ** 3 / dtw / 1e9
 
     line = {
         "metric": "sgemm_fp32_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
