@@ -59,7 +59,8 @@ struct b200mm_kernel {
     void* ws = nullptr;
     size_t ws_bytes = 0;
     // tc3x
-    float *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
+    float *a_lo = nullptr, *b_lo = nullptr;  // lo parts of the operands (the raw operands are consumed as hi)
+    float* b_hi = nullptr;                   // padded copy of B, only when N % 32 != 0
     CUtensorMap tmAh{}, tmAl{}, tmBh{}, tmBl{};
     int tc_bn = 256, tc_bk = 32;
     const void *tc_a_src = nullptr, *tc_b_src = nullptr;  // operands the hi tensor maps currently point at
@@ -640,11 +641,9 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
 static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     const size_t M = k->M, N = k->N, K = k->K;
     const int cols = quant ? 16 : 4;
-    const int max_m = quant ? 4 : 8;
     if (M != 1 && M != 2 && M != 4 && !(M == 8 && !quant))
         return fail(ctx, B200MM_ERR_INVALID, "%s takes M in {1, 2, 4%s} rows of x (skinny GEMM); use an SGEMM kernel for larger M", b200mm_kernel_name(k->id),
                     quant ? "" : ", 8");
-    (void)max_m;
     const int mrows = (int)M;
     if (N % cols || K % 4)
         return fail(ctx, B200MM_ERR_INVALID, "%s needs N%%%d==0 and K%%4==0", b200mm_kernel_name(k->id), cols);

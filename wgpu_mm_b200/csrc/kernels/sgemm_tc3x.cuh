@@ -47,26 +47,10 @@ __device__ __forceinline__ float to_tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
-__global__ void split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo,
-                                  size_t n4) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < n4; i += stride) {
-        const float4 v = __ldg(x + i);
-        float4 h, l;
-        h.x = to_tf32_rna(v.x); l.x = to_tf32_rna(v.x - h.x);
-        h.y = to_tf32_rna(v.y); l.y = to_tf32_rna(v.y - h.y);
-        h.z = to_tf32_rna(v.z); l.z = to_tf32_rna(v.z - h.z);
-        h.w = to_tf32_rna(v.w); l.w = to_tf32_rna(v.w - h.w);
-        hi[i] = h;
-        lo[i] = l;
-    }
-}
-
-// Production split: the tensor core TRUNCATES the low 13 mantissa bits of a kind::tf32 operand (measured,
+// The tensor core TRUNCATES the low 13 mantissa bits of a kind::tf32 operand (measured,
 // tools/probe_tc.py), so the raw fp32 operand already acts as hi = trunc(x) and only lo = tf32(x - trunc(x))
 // has to be materialised (x - trunc(x) is exact in fp32).  One launch covers A and B: reads 2 x 64 MB and
-// writes 2 x 64 MB at 4096^3 instead of 2 x 64 / 4 x 64 for the hi+lo version above.
+// writes 2 x 64 MB at 4096^3 (a version that also materialised hi wrote 4 x 64 MB).
 __global__ void split_lo_kernel(const float4* __restrict__ a, float4* __restrict__ a_lo, size_t a4,
                                 const float4* __restrict__ b, float4* __restrict__ b_lo, size_t b4) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

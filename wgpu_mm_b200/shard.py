@@ -102,7 +102,6 @@ class ShardedSgemm:
         self.Bp.fill_weights_2d(seed + 2, K, Np, N, plan.col0)
         self.C = ctx.buffer(M * N * 4)  # full result, cudaMalloc'd by the library so it can be IPC-exported
         self.peers = []
-        self._flag = torch.zeros(1, device="cuda")
         if mode == "fused":
             self.kern = ctx.kernel(kid, M, Np, K, w.KernelParams(flags=int(w.Flags.PEER_STORE), tune=(tc_bn, 0, 0, 0)))
             handles = [None] * plan.world
@@ -236,7 +235,6 @@ class ShardedGemv:
             self.W.fill_weights_2d(seed + 2, K, Np, N, plan.col0)
         self.y = ctx.buffer(N * 4)
         self.peers = []
-        self._flag = torch.zeros(1, device="cuda")
         kid = w.KernelId.QGEMV_SINT8 if quant else w.KernelId.GEMV_F32
         self.kern = ctx.kernel(kid, 1, Np, K, w.KernelParams(absmax=absmax, batch=1))
         if mode == "fused":
