@@ -265,7 +265,7 @@ def run_single(args):
         ctx.mm_host(kern, npA, npB, npC, dA, dB, dC)  # blocking: returns when C is in host memory
     e2e_s = (time.perf_counter() - te) / e2e_steps
     e2e = {"value": flop / e2e_s / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": M * K * 4 + K * N * 4, "d2h_bytes_per_step": M * N * 4,
-           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "api": "b200mm_mm_host (pinned host A,B -> device, split_lo + tcgen05 GEMM, C -> pinned host; copies pipelined over 8 row panels)"}
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "api": "b200mm_mm_host (pinned host A,B -> device, split_lo + tcgen05 GEMM, C -> pinned host; copies pipelined over 16 row panels)"}
     checksum = float(npC[:4096].astype(np.float64).sum())
     for h in (hA, hB, hC):
         w.lib().b200mm_host_free(h)
