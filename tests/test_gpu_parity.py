@@ -421,3 +421,37 @@ def test_repeatability_stress(gpu_ctx, oracle, case):
     for b in outs + [dA, dB]:
         b.free()
     kern.free()
+
+
+@pytest.mark.parametrize("kid_name", ["SGEMM_TC3X", "SGEMM_SIMT"])
+def test_sgemm_long_k_accuracy(gpu_ctx, oracle, kid_name):
+    """K = 16384 (the depth of BASELINE config 4): the chained TMEM accumulation must hold fp32-level accuracy."""
+    import wgpu_mm_b200 as w
+    M, N, K = 256, 512, 16384
+    A = oracle.generate_weight_data(81, M, K)
+    B = oracle.generate_weight_data(82, K, N)
+    got = _run(gpu_ctx, getattr(w.KernelId, kid_name), A, B, M, N, K)
+    rel = _check(oracle, got, A, B)
+    assert rel <= REL_F64
+
+
+def test_invalid_arguments_are_rejected(gpu_ctx):
+    """Empty shapes, unknown kernels and bad launch grids fail with a status instead of undefined behaviour."""
+    import wgpu_mm_b200 as w
+    for dims in ((0, 64, 64), (64, 0, 64), (64, 64, 0)):
+        with pytest.raises(w.B200mmError):
+            gpu_ctx.kernel(w.KernelId.SGEMM_SIMT, *dims)
+    with pytest.raises(w.B200mmError):
+        gpu_ctx.kernel(999, 64, 64, 64)
+    with pytest.raises(w.B200mmError):
+        gpu_ctx.kernel(w.KernelId.GEMM_5, 48, 64, 64)  # gemm_5.wgsl has no guards: needs M, N % 32 == 0
+    with pytest.raises(w.B200mmError):
+        gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 1, 100, 64, w.KernelParams(absmax=2.0))  # N % 16 != 0
+    kern = gpu_ctx.kernel(w.KernelId.GEMM_1, 64, 64, 64, w.KernelParams(workgroup_size=(16, 16, 1)))
+    buf = gpu_ctx.buffer(64 * 64 * 4)
+    with pytest.raises(w.B200mmError):
+        gpu_ctx.launch(kern, buf, buf, buf, grid=(0, 1, 1))  # "Compute limits exceeded"
+    with pytest.raises(w.B200mmError):
+        gpu_ctx.kernel(w.KernelId.GEMM_1, 64, 64, 64, w.KernelParams(workgroup_size=(64, 64, 1)))  # 4096 threads per workgroup
+    buf.free()
+    kern.free()
