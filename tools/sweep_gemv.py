@@ -48,8 +48,10 @@ if os.environ.get("ONLY_Q"):
 for name, kid, K, N, nsets, quant in CASES:
     print(name, flush=True)
     variants = list(range(int(os.environ.get("NVARIANTS", "4"))))
+    if os.environ.get("VARIANTS"):
+        variants = [int(v) for v in os.environ["VARIANTS"].split(",")]
     for variant in variants:
-        for splits in (0, 4, 6, 8, 10, 12, 16, 20, 24, 32, 40):
+        for splits in (0, 2, 3, 4, 5, 6, 8):
             try:
                 gbps, us, b2b, g, blk = run(kid, K, N, nsets, variant, splits, quant)
             except w.B200mmError as e:
