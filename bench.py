@@ -192,7 +192,7 @@ def time_back_to_back(ctx, kern, sets, iters, warmup):
     return ctx.timer_end() / iters
 
 
-def make_sets(ctx, M, N, K, nsets, seed0, quant=False, oracle=None):
+def make_sets(ctx, M, N, K, nsets, seed0, quant=False, oracle=None, group_k=0):
     sets = []
     for s in range(nsets):
         a = ctx.buffer(M * K * 4); a.fill_weights(seed0 + 10 * s + 1, M * K)
@@ -200,7 +200,7 @@ def make_sets(ctx, M, N, K, nsets, seed0, quant=False, oracle=None):
             import wgpu_mm_b200 as w
             Wm = np.empty((K, N), dtype=np.float32)
             tmp = ctx.buffer(K * N * 4); tmp.fill_weights(seed0 + 10 * s + 2, K * N); tmp.read_into(Wm.reshape(-1)); tmp.free()
-            words, _ = w.quant.sint8_quantize(Wm, K, N)
+            words = w.quant.sint8_quantize_grouped(Wm, K, N, group_k) if group_k else w.quant.sint8_quantize(Wm, K, N)[0]
             b = ctx.buffer_from(words)
         else:
             b = ctx.buffer(K * N * 4); b.fill_weights(seed0 + 10 * s + 2, K * N)
@@ -309,6 +309,16 @@ def run_single(args):
                                             "roofline": {"bound": "hbm", "achieved": qbytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                                          "frac": qbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic.get("gemv_stream_kernel<GemvS8>@4096x14336"),
                                                          "algorithmic_bytes": qbytes, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['_source']})"}}
+        kq.free(); free_sets(qsets)
+        # ---------------- same shape with per-group scales (group_k = 128): weights + 1.8 MB of scales ----------------
+        gk = 128
+        qsets = make_sets(ctx, 1, Nq, Kq, 8, 600, quant=True, group_k=gk)
+        kq = ctx.kernel(w.KernelId.QGEMV_SINT8, 1, Nq, Kq, w.KernelParams(batch=1, group_k=gk))
+        ms = time_back_to_back(ctx, kq, qsets, 400, 40)
+        gqbytes = qbytes + 4.0 * (Kq // gk) * Nq
+        extras["qgemv_sint8_g128_4096x14336"] = {"gbps": gqbytes / (ms * 1e-3) / 1e9, "kernel_us": ms * 1e3, "algorithmic_bytes": gqbytes,
+                                                 "frac_of_hbm_peak": gqbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                                 "timing": "400 back-to-back PDL launches, 8 weight sets rotated"}
         kq.free(); free_sets(qsets)
 
     if not args.no_extras:

@@ -103,6 +103,7 @@ constexpr float ABSMAX = 2.0f;  // src/gemv.rs:8 (the reference dequantises with
 Dims insert_matrix_dims(Context& context, Dims override_dims = Dims{0, 0, 0});  // default (1,1024,1024)
 std::pair<Workload, KernelSpec> qgemv_1(Context& context);      // src/gemv.rs:17-33
 std::pair<Workload, KernelSpec> qgemv_sint8(Context& context);  // B200-native streaming kernel
+std::pair<Workload, KernelSpec> qgemv_sint8_grouped(Context& context, uint32_t group_k = 128);  // per-group scales
 std::pair<Workload, KernelSpec> gemv_f32(Context& context);     // B200-native fp32 GEMV (no reference shader)
 }  // namespace gemv
 
@@ -111,6 +112,19 @@ namespace quant {
 std::pair<std::vector<uint32_t>, float> sint8_quantize(const std::vector<float>& matrix, size_t K, size_t N);
 // src/quant.rs:30-43
 std::vector<float> sint8_dequantize(const std::vector<uint32_t>& quantized, float absmax, size_t K, size_t N);
+
+// Per-group scales (extension of src/quant.rs:17's single global absmax): one absmax per column n and
+// per block of group_k consecutive rows.  `packed` is the device format the grouped sint8 GEMV consumes: the K*N/4 weight
+// words in the src/quant.rs:20-26 layout, followed by ceil(K/group_k)*N f32 scales (bit-cast into the same u32 vector).
+struct GroupedSint8 {
+    std::vector<uint32_t> packed;
+    size_t K = 0, N = 0, group_k = 0;
+    size_t groups() const { return (K + group_k - 1) / group_k; }
+    const uint32_t* words() const { return packed.data(); }
+    const float* scales() const { return reinterpret_cast<const float*>(packed.data() + K * N / 4); }
+};
+GroupedSint8 sint8_quantize_grouped(const std::vector<float>& matrix, size_t K, size_t N, size_t group_k);
+std::vector<float> sint8_dequantize_grouped(const GroupedSint8& q);
 }  // namespace quant
 
 // ---- src/harness.rs ------------------------------------------------------------------------------

@@ -36,6 +36,11 @@ WGPUMM_API int wgpumm_entry_workload(const char* name, size_t M, size_t N, size_
 WGPUMM_API int wgpumm_sint8_quantize(const float* matrix, size_t K, size_t N, uint32_t* out, float* absmax);
 /* src/quant.rs:30-43 */
 WGPUMM_API int wgpumm_sint8_dequantize(const uint32_t* quantized, float absmax, size_t K, size_t N, float* out);
+/* Per-group scales (extension of src/quant.rs:17): `packed` receives K*N/4 weight words followed by
+ * ceil(K/group_k)*N f32 scales -- the B buffer of a qgemv_sint8 kernel created with params.group_k = group_k. */
+WGPUMM_API size_t wgpumm_sint8_grouped_words(size_t K, size_t N, size_t group_k);
+WGPUMM_API int wgpumm_sint8_quantize_grouped(const float* matrix, size_t K, size_t N, size_t group_k, uint32_t* packed);
+WGPUMM_API int wgpumm_sint8_dequantize_grouped(const uint32_t* packed, size_t K, size_t N, size_t group_k, float* out);
 /* src/workload.rs:48-68; dim 0/1/2 = X/Y/Z; returns B200MM_ERR_LIMITS for "Compute limits exceeded". */
 WGPUMM_API int wgpumm_compute_dim(size_t work_items, int dim, uint32_t* count, uint32_t* size);
 WGPUMM_API size_t wgpumm_workload_ceil(size_t num, size_t div);

@@ -535,6 +535,63 @@ ORACLE_API void oracle_qgemv_f64(const float* A, const uint32_t* Bq, double* C, 
     free(Bd);
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Per-group scales (an EXTENSION, the reference only has the global absmax of
+ * src/quant.rs:17).  Same codec as oracle_sint8_quantize, but the absmax is taken per column n and
+ * per block of group_k consecutive rows k: scales[g*N + n] = max |matrix[k*N + n]|, k in group g.
+ * The last group may be ragged.  An all-zero group gives 0/0 = NaN -> `as i32` = 0, like the
+ * reference would for an all-zero matrix.  Nothing in the reference pins this format.
+ * ------------------------------------------------------------------------------------------ */
+ORACLE_API void oracle_sint8_quantize_grouped(const float* matrix, size_t K, size_t N, size_t group_k, uint32_t* out,
+                                              float* scales) {
+    const size_t groups = (K + group_k - 1) / group_k;
+    for (size_t g = 0; g < groups; ++g)
+        for (size_t n = 0; n < N; ++n) {
+            float m = 0.f;
+            for (size_t k = g * group_k; k < K && k < (g + 1) * group_k; ++k) {
+                float a = fabsf(matrix[k * N + n]);
+                if (a > m) m = a;
+            }
+            scales[g * N + n] = m;
+        }
+    for (size_t k = 0; k < K; ++k)
+        for (size_t n = 0; n < N; n += 4) {
+            uint32_t w = 0;
+            for (int j = 0; j < 4; ++j) {
+                float q = roundf(matrix[k * N + n + j] / scales[(k / group_k) * N + n + j] * 127.f);
+                w |= ((uint32_t)rust_f32_as_i32(q) & 0xFFu) << (8 * j);
+            }
+            out[(k * N + n) / 4] = w;
+        }
+}
+
+ORACLE_API void oracle_sint8_dequantize_grouped(const uint32_t* q, const float* scales, size_t K, size_t N, size_t group_k,
+                                                float* out) {
+    for (size_t k = 0; k < K; ++k)
+        for (size_t n = 0; n < N; ++n) {
+            uint32_t w = q[(k * N + n) / 4];
+            int8_t b = (int8_t)((w >> (8 * (n & 3))) & 0xFFu);
+            out[k * N + n] = (float)b / 127.0f * scales[(k / group_k) * N + n];
+        }
+}
+
+/* mm_ref / FP64 GEMM over the group-dequantised weights (same construction as oracle_qgemv_ref / _f64). */
+ORACLE_API void oracle_qgemv_grouped_ref(const float* A, const uint32_t* Bq, const float* scales, float* C, size_t M, size_t N,
+                                         size_t K, size_t group_k) {
+    float* Bd = (float*)malloc(sizeof(float) * K * N);
+    oracle_sint8_dequantize_grouped(Bq, scales, K, N, group_k, Bd);
+    oracle_mm_ref(A, Bd, C, M, N, K);
+    free(Bd);
+}
+
+ORACLE_API void oracle_qgemv_grouped_f64(const float* A, const uint32_t* Bq, const float* scales, double* C, size_t M, size_t N,
+                                         size_t K, size_t group_k) {
+    float* Bd = (float*)malloc(sizeof(float) * K * N);
+    oracle_sint8_dequantize_grouped(Bq, scales, K, N, group_k, Bd);
+    oracle_mm_f64(A, Bd, C, M, N, K);
+    free(Bd);
+}
+
 /* src/workload.rs:48-68 compute_dim.  Returns 0 and fills (count,size), or -1 for the
  * reference's panic!("Compute limits exceeded").  dim: 0=X,1=Y,2=Z. */
 ORACLE_API int oracle_compute_dim(size_t work_items, int dim, uint32_t* count, uint32_t* size) {

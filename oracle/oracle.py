@@ -60,6 +60,10 @@ def _declare(l):
     l.oracle_sint8_quantize.argtypes = [_f32p, _sz, _sz, _u32p]
     l.oracle_sint8_quantize.restype = C.c_float
     l.oracle_sint8_dequantize.argtypes = [_u32p, C.c_float, _sz, _sz, _f32p]
+    l.oracle_sint8_quantize_grouped.argtypes = [_f32p, _sz, _sz, _sz, _u32p, _f32p]
+    l.oracle_sint8_dequantize_grouped.argtypes = [_u32p, _f32p, _sz, _sz, _sz, _f32p]
+    l.oracle_qgemv_grouped_ref.argtypes = [_f32p, _u32p, _f32p, _f32p, _sz, _sz, _sz, _sz]
+    l.oracle_qgemv_grouped_f64.argtypes = [_f32p, _u32p, _f32p, _f64p, _sz, _sz, _sz, _sz]
     l.oracle_wgsl_qgemv_1.argtypes = [_f32p, _u32p, _f32p, _sz, _sz, _sz, C.c_float]
     l.oracle_qgemv_ref.argtypes = [_f32p, _u32p, _f32p, _sz, _sz, _sz, C.c_float]
     l.oracle_qgemv_f64.argtypes = [_f32p, _u32p, _f64p, _sz, _sz, _sz, C.c_float]
@@ -190,6 +194,43 @@ def qgemv_f64(A, Bq, M: int, N: int, K: int, absmax: float) -> np.ndarray:
     b = np.ascontiguousarray(Bq, dtype=np.uint32).reshape(-1)
     out = np.empty((M, N), dtype=np.float64)
     lib().oracle_qgemv_f64(a, b, out, M, N, K, absmax)
+    return out
+
+
+def sint8_quantize_grouped(matrix, K: int, N: int, group_k: int):
+    """Per-(group of group_k rows, column) absmax variant of src/quant.rs:7-28 (extension).
+    -> (uint32 words of K*N/4, float32 scales of ceil(K/group_k) x N)."""
+    m = np.ascontiguousarray(matrix, dtype=np.float32).reshape(-1)
+    assert m.size == K * N and N % 4 == 0 and group_k > 0
+    out = np.empty(K * N // 4, dtype=np.uint32)
+    scales = np.empty((-(-K // group_k), N), dtype=np.float32)
+    lib().oracle_sint8_quantize_grouped(m, K, N, group_k, out, scales.reshape(-1))
+    return out, scales
+
+
+def sint8_dequantize_grouped(words, scales, K: int, N: int, group_k: int) -> np.ndarray:
+    w = np.ascontiguousarray(words, dtype=np.uint32).reshape(-1)
+    s = np.ascontiguousarray(scales, dtype=np.float32).reshape(-1)
+    out = np.empty(K * N, dtype=np.float32)
+    lib().oracle_sint8_dequantize_grouped(w, s, K, N, group_k, out)
+    return out.reshape(K, N)
+
+
+def qgemv_grouped_ref(A, Bq, scales, M: int, N: int, K: int, group_k: int) -> np.ndarray:
+    a = np.ascontiguousarray(A, dtype=np.float32).reshape(-1)
+    b = np.ascontiguousarray(Bq, dtype=np.uint32).reshape(-1)
+    s = np.ascontiguousarray(scales, dtype=np.float32).reshape(-1)
+    out = np.full((M, N), 123.25, dtype=np.float32)
+    lib().oracle_qgemv_grouped_ref(a, b, s, out, M, N, K, group_k)
+    return out
+
+
+def qgemv_grouped_f64(A, Bq, scales, M: int, N: int, K: int, group_k: int) -> np.ndarray:
+    a = np.ascontiguousarray(A, dtype=np.float32).reshape(-1)
+    b = np.ascontiguousarray(Bq, dtype=np.uint32).reshape(-1)
+    s = np.ascontiguousarray(scales, dtype=np.float32).reshape(-1)
+    out = np.empty((M, N), dtype=np.float64)
+    lib().oracle_qgemv_grouped_f64(a, b, s, out, M, N, K, group_k)
     return out
 
 

@@ -14,6 +14,7 @@ pub struct b200mm_kernel_params {
     pub batch: u32,
     pub flags: u32,
     pub tune: [u32; 4],
+    pub group_k: u32,
 }
 
 pub const B200MM_K_GEMM_1: c_int = 1;

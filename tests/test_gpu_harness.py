@@ -59,6 +59,18 @@ def test_qgemv_llm_shape(gpu_ctx):
     assert rep.max_abs_err <= 1e-3 and rep.max_rel_err_f64 <= 5e-6
 
 
+@pytest.mark.parametrize("dims", [(1, 1024, 1024), (1, 14336, 4096)])
+def test_qgemv_grouped_scales(gpu_ctx, dims):
+    """Per-group scales (group_k = 128) through the same harness: quantise, launch, gate against mm_ref."""
+    from wgpu_mm_b200 import gemv, harness
+    context = {}
+    dims = gemv.insert_matrix_dims(context, dims)
+    workload, shader = gemv.qgemv_sint8_grouped(context)
+    rep = harness.test_harness(workload, shader, dims, True)
+    assert rep.max_abs_err <= 1e-3 and rep.max_rel_err_f64 <= 5e-6
+    assert rep.kernel_gbps > 0
+
+
 def test_mae_gate_panics(gpu_ctx):
     """A kernel that misses the gate must panic with the reference's message: single-pass TF32 at K=4096."""
     import ctypes as C

@@ -256,6 +256,82 @@ def test_qgemv_batched(gpu_ctx, oracle, kid_name):
         assert oracle.max_abs_err(got[b:b + 1], oracle.qgemv_ref(x[b:b + 1], Ws[b], 1, N, K, 2.0)) <= GATE
 
 
+GROUPED = [(1024, 1024, 128), (4096, 14336, 128), (4096, 14336, 256), (1000, 1040, 128), (64, 64, 128), (2048, 512, 2048),
+           (1536, 256, 512), (4096, 4096, 4096)]
+
+
+@pytest.mark.parametrize("kng", GROUPED)
+def test_qgemv_sint8_grouped_scales(gpu_ctx, oracle, kng):
+    """Per-(row block, column) scales: B = weight words ++ f32 scales, params.group_k set.
+    Checked against mm_ref / FP64 over the oracle's group-dequantised weights; ragged last group, K < group_k, panels
+    that are not full (N % 256 != 0), one group per column (group_k >= K) included."""
+    import wgpu_mm_b200 as w
+    from wgpu_mm_b200.quant import sint8_quantize_grouped, split_grouped
+    K, N, G = kng
+    x = oracle.generate_weight_data(61, 1, K)
+    W = oracle.generate_weight_data(62, K, N)
+    W *= (1.0 + 7.0 * (np.arange(K, dtype=np.float32)[:, None] // G % 3)) * (1.0 + (np.arange(N, dtype=np.float32)[None, :] % 5))
+    packed = sint8_quantize_grouped(W, K, N, G)
+    words, scales = split_grouped(packed, K, N, G)
+    owords, oscales = oracle.sint8_quantize_grouped(W, K, N, G)  # product codec == oracle codec, bit for bit
+    assert np.array_equal(words, owords) and np.array_equal(scales, oscales)
+    prm = w.KernelParams(batch=1, group_k=G)
+    got = _run(gpu_ctx, w.KernelId.QGEMV_SINT8, x, packed, 1, N, K, prm, b_dtype=np.uint32)
+    assert not np.isnan(got).any()
+    e, m = oracle.err_vs_f64(got, oracle.qgemv_grouped_f64(x, words, scales, 1, N, K, G))
+    assert e / m <= REL_F64, f"rel err vs fp64 {e / m:.3e}"
+    ref = oracle.qgemv_grouped_ref(x, words, scales, 1, N, K, G)
+    assert oracle.max_abs_err(got, ref) <= GATE * max(1.0, m)  # the blown-up weights make |y| > 1: gate relative to max |y|
+
+
+def test_qgemv_grouped_beats_global_scale_on_outliers(gpu_ctx, oracle):
+    """Why the format exists: one outlier weight ruins the global-absmax codec (src/quant.rs:17) for every column."""
+    import wgpu_mm_b200 as w
+    from wgpu_mm_b200.quant import sint8_quantize_grouped
+    K, N, G = 1024, 1024, 128
+    x = oracle.generate_weight_data(63, 1, K)
+    W = oracle.generate_weight_data(64, K, N)
+    W[5, 7] = 40.0
+    full = oracle.mm_f64(x, W)
+    words, absmax = oracle.sint8_quantize(W, K, N)
+    y_global = _run(gpu_ctx, w.KernelId.QGEMV_SINT8, x, words, 1, N, K, w.KernelParams(absmax=absmax, batch=1), b_dtype=np.uint32)
+    y_group = _run(gpu_ctx, w.KernelId.QGEMV_SINT8, x, sint8_quantize_grouped(W, K, N, G), 1, N, K,
+                   w.KernelParams(batch=1, group_k=G), b_dtype=np.uint32)
+    others = np.arange(N) != 7  # the damage is confined to the outlier's own (row block, column)
+    err_global = np.abs(y_global - full)[0, others].max()
+    err_group = np.abs(y_group - full)[0, others].max()
+    assert err_group < 0.02 and err_group * 10 < err_global, (err_group, err_global)
+    assert np.abs(y_group - full)[0, 7] <= np.abs(y_global - full).max() * 1.5
+
+
+def test_qgemv_grouped_batched_and_errors(gpu_ctx, oracle):
+    import wgpu_mm_b200 as w
+    from wgpu_mm_b200.quant import sint8_quantize_grouped, split_grouped
+    K, N, G, batch = 512, 512, 128, 2
+    x = oracle.generate_weight_data(65, batch, K)
+    packs = [sint8_quantize_grouped(oracle.generate_weight_data(70 + b, K, N), K, N, G) for b in range(batch)]
+    got = _run(gpu_ctx, w.KernelId.QGEMV_SINT8, x, np.concatenate(packs), 1, N, K, w.KernelParams(batch=batch, group_k=G), b_dtype=np.uint32)
+    for b in range(batch):
+        words, scales = split_grouped(packs[b], K, N, G)
+        e, m = oracle.err_vs_f64(got[b:b + 1], oracle.qgemv_grouped_f64(x[b:b + 1], words, scales, 1, N, K, G))
+        assert e / m <= REL_F64
+    with pytest.raises(w.B200mmError):
+        gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 1, N, K, w.KernelParams(group_k=96))  # not a multiple of 128
+    with pytest.raises(w.B200mmError):
+        gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 2, N, K, w.KernelParams(group_k=128))  # M > 1
+    with pytest.raises(w.B200mmError):
+        gpu_ctx.kernel(w.KernelId.GEMV_F32, 1, N, K, w.KernelParams(group_k=128))  # fp32 weights carry no scales
+    kern = gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 1, N, K, w.KernelParams(group_k=G))
+    dA = gpu_ctx.buffer_from(x[:1].copy())
+    dB = gpu_ctx.buffer_from(split_grouped(packs[0], K, N, G)[0].copy())  # weights without their scales: too short
+    dC = gpu_ctx.buffer_from(np.zeros(N, dtype=np.float32))
+    with pytest.raises(w.B200mmError):
+        gpu_ctx.launch(kern, dA, dB, dC)
+    for b in (dA, dB, dC):
+        b.free()
+    kern.free()
+
+
 def test_device_datagen_matches_oracle(gpu_ctx, oracle):
     n = 1 << 16
     buf = gpu_ctx.buffer(n * 4)

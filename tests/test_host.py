@@ -137,3 +137,50 @@ def test_cpp_runner_reports_like_cargo(built_lib):
     assert os.path.exists(exe)
     r = subprocess.run([exe, "test_qdq"], capture_output=True, text=True)
     assert r.returncode == 0 and "test test_qdq ... ok" in r.stdout
+
+
+@pytest.mark.parametrize("kng", [(256, 64, 128), (300, 16, 128), (64, 8, 128), (512, 32, 512)])
+def test_grouped_codec_matches_oracle(oracle, kng):
+    """Per-group scales (extension of src/quant.rs:17): product codec (host/quant.cc) == oracle restatement, bit for bit;
+    the round trip is within half a quantisation step of each group's own scale."""
+    from wgpu_mm_b200.quant import sint8_dequantize_grouped, sint8_quantize_grouped, split_grouped
+    K, N, G = kng
+    W = oracle.generate_weight_data(90, K, N)
+    W[: K // 2] *= 9.0
+    W[3, :] = 0.0
+    packed = sint8_quantize_grouped(W, K, N, G)
+    words, scales = split_grouped(packed, K, N, G)
+    owords, oscales = oracle.sint8_quantize_grouped(W, K, N, G)
+    assert np.array_equal(words, owords) and np.array_equal(scales, oscales)
+    assert scales.shape == (-(-K // G), N)
+    back = sint8_dequantize_grouped(packed, K, N, G)
+    assert np.array_equal(back, oracle.sint8_dequantize_grouped(owords, oscales, K, N, G))
+    step = np.repeat(scales, G, axis=0)[:K] / 127.0
+    assert (np.abs(back - W) <= 0.5 * step + 1e-7).all()
+
+
+def test_grouped_codec_one_group_equals_per_column_global(oracle):
+    """group_k >= K: one scale per column; a column whose absmax equals the matrix absmax packs exactly like src/quant.rs."""
+    from wgpu_mm_b200.quant import sint8_quantize, sint8_quantize_grouped, split_grouped
+    K, N = 64, 16
+    W = oracle.generate_weight_data(91, K, N)
+    W[0, :] = 0.25  # every column now has the same absmax = the global one
+    words, scales = split_grouped(sint8_quantize_grouped(W, K, N, 128), K, N, 128)
+    gwords, absmax = sint8_quantize(W, K, N)
+    assert absmax == 0.25 and (scales == 0.25).all() and np.array_equal(words, gwords)
+
+
+def test_grouped_codec_zero_group_and_asserts():
+    from wgpu_mm_b200 import B200mmError
+    from wgpu_mm_b200.quant import sint8_dequantize_grouped, sint8_quantize_grouped, split_grouped
+    W = np.zeros((128, 8), dtype=np.float32)
+    packed = sint8_quantize_grouped(W, 128, 8, 128)  # 0/0 = NaN -> `as i32` = 0, like the reference on an all-zero matrix
+    words, scales = split_grouped(packed, 128, 8, 128)
+    assert not words.any() and not scales.any()
+    assert not sint8_dequantize_grouped(packed, 128, 8, 128).any()
+    with pytest.raises(B200mmError):
+        sint8_quantize_grouped(W, 128, 6, 128)
+    with pytest.raises(B200mmError):
+        sint8_quantize_grouped(W, 128, 8, 0)
+    with pytest.raises(B200mmError):
+        sint8_dequantize_grouped(packed[:-1], 128, 8, 128)

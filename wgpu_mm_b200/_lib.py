@@ -55,6 +55,7 @@ class KernelParamsC(C.Structure):
         ("batch", C.c_uint32),
         ("flags", C.c_uint32),
         ("tune", C.c_uint32 * 4),
+        ("group_k", C.c_uint32),
     ]
 
 
@@ -152,6 +153,10 @@ def _declare(l: C.CDLL) -> None:
     l.wgpumm_entry_workload.argtypes = [C.c_char_p, sz, sz, sz, u32p, u32p, C.POINTER(C.c_int)]
     l.wgpumm_sint8_quantize.argtypes = [vp, sz, sz, vp, C.POINTER(C.c_float)]
     l.wgpumm_sint8_dequantize.argtypes = [vp, C.c_float, sz, sz, vp]
+    l.wgpumm_sint8_grouped_words.restype = sz
+    l.wgpumm_sint8_grouped_words.argtypes = [sz, sz, sz]
+    l.wgpumm_sint8_quantize_grouped.argtypes = [vp, sz, sz, sz, vp]
+    l.wgpumm_sint8_dequantize_grouped.argtypes = [vp, sz, sz, sz, vp]
     l.wgpumm_compute_dim.argtypes = [sz, C.c_int, u32p, u32p]
     l.wgpumm_workload_ceil.restype = sz
     l.wgpumm_workload_ceil.argtypes = [sz, sz]

@@ -18,6 +18,7 @@ class KernelParams:
     batch: int = 0
     flags: int = 0
     tune: Sequence[int] = field(default_factory=lambda: (0, 0, 0, 0))
+    group_k: int = 0
 
     def to_c(self) -> KernelParamsC:
         p = KernelParamsC()
@@ -29,6 +30,7 @@ class KernelParams:
         t = list(self.tune) + [0, 0, 0, 0]
         for i in range(4):
             p.tune[i] = int(t[i])
+        p.group_k = int(self.group_k)
         return p
 
 

@@ -402,8 +402,16 @@ using Tc256x1 = Tc3xCfg<256, 4, true, 32>;
 // gemv variants: 0: 8 warps, unroll 8, full-warp rows;  1: 8 warps, unroll 8, half-warp rows
 template <class T>
 static void gemv_pick(int variant, void (**fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float,
-                                               size_t, size_t, size_t, PeerStore, int),
-                      int* warps, int* lpr, int mrows = 1) {
+                                               size_t, size_t, size_t, PeerStore, int, int),
+                      int* warps, int* lpr, int mrows = 1, bool grouped = false) {
+    if constexpr (T::COLS == 16) {
+        if (grouped) {  // per-group scales: the default sint8 geometry only (window = 2 * 4 * 16 = 128 rows)
+            *fn = gemv_stream_kernel<T, 8, 4, 16, 1, true>;
+            *warps = 8;
+            *lpr = 16;
+            return;
+        }
+    }
     if (mrows > 1) {
         // skinny GEMM: only the default geometry of each weight type is instantiated for M = 2, 4, 8
         if constexpr (T::COLS == 4) {
@@ -651,10 +659,17 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     if (N > INT32_MAX || K > INT32_MAX) return fail(ctx, B200MM_ERR_INVALID, "shape too large");
     // tune[0]: 0 = default for the weight type (measured on B200, tools/sweep_gemv.py), 100 = variant 0, else the variant id
     k->gemv_variant = k->prm.tune[0] == 0 ? (quant ? 4 : 5) : (k->prm.tune[0] == 100 ? 0 : (int)k->prm.tune[0]);
-    void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t, PeerStore, int);
+    void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t, PeerStore, int, int);
     int warps, lpr;
+    const size_t group_k = k->prm.group_k;
+    if (group_k) {  // per-(row block, column) scales stored behind the weights
+        if (!quant) return fail(ctx, B200MM_ERR_INVALID, "group_k applies to qgemv_sint8 only");
+        if (M != 1) return fail(ctx, B200MM_ERR_INVALID, "qgemv_sint8 with group_k: M must be 1");
+        if (group_k % 128) return fail(ctx, B200MM_ERR_INVALID, "qgemv_sint8: group_k must be a multiple of 128 (got %zu)", group_k);
+        if (k->prm.flags & B200MM_F_PEER_STORE) return fail(ctx, B200MM_ERR_INVALID, "qgemv_sint8 with group_k: peer stores not supported");
+    }
     if (quant)
-        gemv_pick<GemvS8>(k->gemv_variant, &fn, &warps, &lpr, mrows);
+        gemv_pick<GemvS8>(k->gemv_variant, &fn, &warps, &lpr, mrows, group_k != 0);
     else
         gemv_pick<GemvF32>(k->gemv_variant, &fn, &warps, &lpr, mrows);
     const int panel = lpr * cols;
@@ -684,7 +699,7 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
         else
             splits = 8;
     }
-    const int rstep = warps * (32 / lpr);
+    const int rstep = group_k ? 128 : warps * (32 / lpr);  // grouped: splits start on a pipeline-window boundary
     size_t rps = ceil_div(K, (size_t)splits);
     rps = ceil_div(rps, rstep) * rstep;
     splits = (int)ceil_div(K, rps);
@@ -693,6 +708,7 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     k->grid = dim3(k->panels, splits, batch);
     k->block = dim3(warps * 32, 1, 1);
     k->smem = ((size_t)mrows * rps + (size_t)warps * mrows * panel + (size_t)mrows * panel) * sizeof(float);
+    if (group_k) k->smem += (rps / group_k + 2) * panel * sizeof(float);
     if (k->smem > 200 * 1024) return fail(ctx, B200MM_ERR_INVALID, "gemv: K-split too long for shared memory");
     CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(k->smem, 48 * 1024)));
     if (splits > 1 && !k->gemv_cluster) {
@@ -936,14 +952,15 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
         case B200MM_K_GEMV_F32:
         case B200MM_K_QGEMV_SINT8: {
             const bool quant = k->id == B200MM_K_QGEMV_SINT8;
-            void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t, PeerStore, int);
+            void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t, PeerStore, int, int);
             int warps, lpr;
             if (quant)
-                gemv_pick<GemvS8>(k->gemv_variant, &fn, &warps, &lpr, (int)k->M);
+                gemv_pick<GemvS8>(k->gemv_variant, &fn, &warps, &lpr, (int)k->M, k->prm.group_k != 0);
             else
                 gemv_pick<GemvF32>(k->gemv_variant, &fn, &warps, &lpr, (int)k->M);
-            const float scale = quant ? k->prm.absmax / 127.0f : 1.0f;
-            const size_t wstride = quant ? (size_t)K * N : (size_t)K * N * 4;
+            const size_t group_k = k->prm.group_k;
+            const float scale = quant ? (group_k ? 1.0f : k->prm.absmax) / 127.0f : 1.0f;
+            const size_t wstride = quant ? (size_t)K * N + (group_k ? ceil_div(K, group_k) * N * 4 : 0) : (size_t)K * N * 4;
             if (k->peers.world && (k->prm.batch > 1 || k->M > 1)) return fail(ctx, B200MM_ERR_INVALID, "peer stores are not supported for batched / multi-row GEMV");
             // launched with programmatic stream serialization (PDL): see the griddepcontrol comments in gemv.cuh
             cudaLaunchConfig_t cfg{};
@@ -965,7 +982,7 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
                 cfg.numAttrs = 2;
             }
             CU_TRY(ctx, cudaLaunchKernelEx(&cfg, fn, Af, (const void*)B, Cf, k->partial, k->tickets, (int)K, (int)N, k->rows_per_split, scale,
-                                           (size_t)k->M * K, wstride, (size_t)k->M * N, k->peers, cluster ? 1 : 0));
+                                           (size_t)k->M * K, wstride, (size_t)k->M * N, k->peers, cluster ? 1 : 0, (int)group_k));
             break;
         }
         default:
@@ -979,6 +996,7 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
 
 static size_t b_bytes_needed(const b200mm_kernel* k) {
     const size_t batch = k->prm.batch ? k->prm.batch : 1;
+    if (k->id == B200MM_K_QGEMV_SINT8 && k->prm.group_k) return batch * (k->K * k->N + ceil_div(k->K, (size_t)k->prm.group_k) * k->N * 4);
     if (k->id == B200MM_K_QGEMV_1 || k->id == B200MM_K_QGEMV_SINT8) return batch * k->K * k->N;
     if (k->id == B200MM_K_GEMV_F32) return batch * k->K * k->N * 4;
     return k->K * k->N * 4;

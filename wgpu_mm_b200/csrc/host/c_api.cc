@@ -28,6 +28,7 @@ static const Entry* find_entry(const char* name) {
         {"sgemm_simt", gemm::sgemm_simt, false, false}, {"sgemm_tc3x", gemm::sgemm_tc3x, false, false},
         {"qgemv_1", gemv::qgemv_1, true, true},         {"qgemv_sint8", gemv::qgemv_sint8, true, true},
         {"gemv_f32", gemv::gemv_f32, true, false},
+        {"qgemv_sint8_grouped", [](Context& c) { return gemv::qgemv_sint8_grouped(c, 128); }, true, true},
     };
     for (const auto& e : table)
         if (!strcmp(e.name, name)) return &e;
@@ -122,6 +123,40 @@ extern "C" int wgpumm_sint8_dequantize(const uint32_t* quantized, float absmax, 
         if (!quantized || !out) throw Panic("NULL argument");
         std::vector<uint32_t> q(quantized, quantized + K * N / 4);
         auto m = quant::sint8_dequantize(q, absmax, K, N);
+        memcpy(out, m.data(), m.size() * sizeof(float));
+    } catch (const std::exception& ex) {
+        g_panic = ex.what();
+        return B200MM_ERR_INVALID;
+    }
+    return B200MM_OK;
+}
+
+extern "C" size_t wgpumm_sint8_grouped_words(size_t K, size_t N, size_t group_k) {
+    return group_k ? K * N / 4 + (K + group_k - 1) / group_k * N : 0;
+}
+
+extern "C" int wgpumm_sint8_quantize_grouped(const float* matrix, size_t K, size_t N, size_t group_k, uint32_t* packed) {
+    try {
+        if (!matrix || !packed) throw Panic("NULL argument");
+        std::vector<float> m(matrix, matrix + K * N);
+        auto q = quant::sint8_quantize_grouped(m, K, N, group_k);
+        memcpy(packed, q.packed.data(), q.packed.size() * sizeof(uint32_t));
+    } catch (const std::exception& ex) {
+        g_panic = ex.what();
+        return B200MM_ERR_INVALID;
+    }
+    return B200MM_OK;
+}
+
+extern "C" int wgpumm_sint8_dequantize_grouped(const uint32_t* packed, size_t K, size_t N, size_t group_k, float* out) {
+    try {
+        if (!packed || !out) throw Panic("NULL argument");
+        quant::GroupedSint8 q;
+        q.K = K;
+        q.N = N;
+        q.group_k = group_k;
+        q.packed.assign(packed, packed + wgpumm_sint8_grouped_words(K, N, group_k));
+        auto m = quant::sint8_dequantize_grouped(q);
         memcpy(out, m.data(), m.size() * sizeof(float));
     } catch (const std::exception& ex) {
         g_panic = ex.what();

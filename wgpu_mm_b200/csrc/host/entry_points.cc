@@ -153,6 +153,14 @@ std::pair<Workload, KernelSpec> qgemv_sint8(Context& c) {
     r.second.params.batch = 1;
     return r;
 }
+std::pair<Workload, KernelSpec> qgemv_sint8_grouped(Context& c, uint32_t group_k) {
+    auto r = qgemv_sint8(c);
+    r.second.name = "qgemv_sint8_grouped";
+    r.second.params.absmax = 0.f;  // every (row block, column) carries its own scale behind the weights
+    r.second.params.group_k = group_k;
+    c["group_k"] = group_k;
+    return r;
+}
 std::pair<Workload, KernelSpec> gemv_f32(Context& c) {
     size_t M, N, K;
     need_dims(c, M, N, K);

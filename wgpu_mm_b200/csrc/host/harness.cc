@@ -153,9 +153,15 @@ HarnessReport test_harness(const Workload& workload, const KernelSpec& shader, D
             // rand_quantized_gpu_buffer: the true absmax is discarded (src/harness.rs:134) and both sides
             // dequantise with gemv::ABSMAX (src/harness.rs:44, src/gemv.rs:30) -- kept for drop-in parity
             std::vector<float> w = generate_weight_data(opt.seed + 2, K, N);
-            auto q = quant::sint8_quantize(w, K, N);
-            B = make_buffer(q.first.data(), q.first.size() * 4);
-            B_cpu = quant::sint8_dequantize(q.first, gemv::ABSMAX, K, N);
+            if (prm.group_k) {  // per-group scales travel with the weights, so both sides use the TRUE scales
+                auto q = quant::sint8_quantize_grouped(w, K, N, prm.group_k);
+                B = make_buffer(q.packed.data(), q.packed.size() * 4);
+                B_cpu = quant::sint8_dequantize_grouped(q);
+            } else {
+                auto q = quant::sint8_quantize(w, K, N);
+                B = make_buffer(q.first.data(), q.first.size() * 4);
+                B_cpu = quant::sint8_dequantize(q.first, gemv::ABSMAX, K, N);
+            }
         } else {
             B_cpu = generate_weight_data(opt.seed + 2, K, N);
             B = make_buffer(B_cpu.data(), B_cpu.size() * 4);
@@ -193,8 +199,13 @@ HarnessReport test_harness(const Workload& workload, const KernelSpec& shader, D
     b200mm_buffer* A = make_buffer(host.data(), host.size() * 4);
     b200mm_buffer* B;
     if (quantize_b) {
-        auto q = quant::sint8_quantize(generate_weight_data(opt.seed + 12, K, N), K, N);
-        B = make_buffer(q.first.data(), q.first.size() * 4);
+        if (prm.group_k) {
+            auto q = quant::sint8_quantize_grouped(generate_weight_data(opt.seed + 12, K, N), K, N, prm.group_k);
+            B = make_buffer(q.packed.data(), q.packed.size() * 4);
+        } else {
+            auto q = quant::sint8_quantize(generate_weight_data(opt.seed + 12, K, N), K, N);
+            B = make_buffer(q.first.data(), q.first.size() * 4);
+        }
     } else {
         host = generate_weight_data(opt.seed + 12, K, N);
         B = make_buffer(host.data(), host.size() * 4);
@@ -232,7 +243,8 @@ HarnessReport test_harness(const Workload& workload, const KernelSpec& shader, D
     rep.gflops = (flops / 1e9) / (rep.wall_ns / 1e9);
     rep.kernel_ms = ms / opt.timed;
     rep.kernel_gflops = ((double)M * N * K * 2 / 1e9) / (rep.kernel_ms / 1e3);
-    const double bytes = (quantize_b ? (double)K * N : (double)K * N * 4) + 4.0 * M * K + 4.0 * M * N;
+    const double scale_bytes = prm.group_k ? 4.0 * (double)((K + prm.group_k - 1) / prm.group_k) * N : 0.0;
+    const double bytes = (quantize_b ? (double)K * N + scale_bytes : (double)K * N * 4) + 4.0 * M * K + 4.0 * M * N;
     rep.kernel_gbps = bytes / 1e9 / (rep.kernel_ms / 1e3);
     if (opt.verbose) {
         printf("%.0f ns\n", rep.wall_ns);

@@ -89,12 +89,19 @@ __device__ __forceinline__ void store_y(float* y, int gc, float v, const PeerSto
 //   panel = LPR * COLS columns;   rows of a split are dealt round-robin to (warp, row-in-warp) slots.
 // partial: [batch][splits][N] floats, tickets: [batch][panels] u32 (zeroed once; self-resetting).
 // MROWS > 1: skinny GEMM -- MROWS rows of x (row-major MROWS x K) share one pass over W; y is MROWS x N.
-template <class T, int WARPS, int UNROLL, int LPR, int MROWS = 1>
-__global__ void __launch_bounds__(WARPS * 32)
+// GROUPED (sint8 only): the K*N weight bytes are followed by ceil(K/group_k) x N f32 scales, one per
+//   (block of group_k rows, column).  A thread's pipeline window of 2*UNROLL*RSTEP rows is aligned so that it never
+//   straddles a group (the host enforces group_k % window == 0 and rows_per_split % window == 0); the integer-valued
+//   partial dot product of a group is folded into the running total with ONE fma per column when the group changes, so
+//   the inner loop is the ungrouped one.  The CTA's scales (<= rows_per_split/group_k + 1 groups x PANEL columns) are
+//   staged in shared memory up front, off the critical path.
+template <class T, int WARPS, int UNROLL, int LPR, int MROWS = 1, bool GROUPED = false>
+__global__ void __launch_bounds__(WARPS * 32, GROUPED ? 3 : 1)
 gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, float* __restrict__ y,
                    float* __restrict__ partial, unsigned int* __restrict__ tickets, int K, int N, int rows_per_split,
                    float out_scale, size_t x_batch_stride, size_t w_batch_stride_bytes, size_t y_batch_stride,
-                   const __grid_constant__ PeerStore peers, int use_cluster) {
+                   const __grid_constant__ PeerStore peers, int use_cluster, int group_k) {
+    static_assert(!GROUPED || MROWS == 1, "grouped scales: single-row kernel only");
     constexpr int COLS = T::COLS;
     constexpr int RPW = 32 / LPR;        // rows per warp per load
     constexpr int RSTEP = WARPS * RPW;   // rows per CTA per load
@@ -138,6 +145,18 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     constexpr bool EAGER = (T::COLS == 4);
     issue(wa, k);
     if constexpr (EAGER) issue(wb, k + UNROLL * RSTEP);
+    // grouped scales of this CTA's rows x columns -> shared memory (weights: independent of the previous kernel)
+    float* ss = red + (WARPS * MROWS + MROWS) * PANEL;
+    const int g0 = GROUPED ? k_beg / group_k : 0;
+    const int ngl = GROUPED ? rows_per_split / group_k + 2 : 0;
+    if constexpr (GROUPED) {
+        const float* sc = reinterpret_cast<const float*>(Wb + (size_t)K * N);
+        const int groups = (K + group_k - 1) / group_k;
+        for (int i = tid; i < ngl * PANEL; i += WARPS * 32) {
+            const int g = g0 + i / PANEL, gc = panel * PANEL + i % PANEL;
+            ss[i] = (g < groups && gc < N) ? __ldg(sc + (size_t)g * N + gc) : 0.f;
+        }
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
 #pragma unroll
@@ -150,6 +169,33 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     for (int m = 0; m < MROWS; ++m)
 #pragma unroll
         for (int j = 0; j < COLS; ++j) acc[m][j] = 0.f;
+    // GROUPED: acc[0] is the current group's partial, tot the scaled running total
+    float tot[GROUPED ? COLS : 1];
+    int cur_g = 0;
+    if constexpr (GROUPED) {
+#pragma unroll
+        for (int j = 0; j < COLS; ++j) tot[j] = 0.f;
+        cur_g = k / group_k;
+    }
+    auto fold = [&](int g) {
+        if constexpr (GROUPED) {
+            const float* s = ss + min(max(g - g0, 0), ngl - 1) * PANEL + lir * COLS;
+#pragma unroll
+            for (int j = 0; j < COLS; ++j) {
+                tot[j] = fmaf(acc[0][j], s[j], tot[j]);
+                acc[0][j] = 0.f;
+            }
+        }
+    };
+    auto group_step = [&](int kk) {  // entering the window whose first row (for this thread) is kk: warp-uniform branch
+        if constexpr (GROUPED) {
+            const int g = kk / group_k;
+            if (g != cur_g) {
+                fold(cur_g);
+                cur_g = g;
+            }
+        }
+    };
 
     auto consume = [&](const typename T::Vec (&w)[UNROLL], int kk) {
 #pragma unroll
@@ -175,6 +221,7 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     if (col_ok) {
         constexpr int AHEAD = (EAGER ? 4 : 3) * UNROLL - 1;  // furthest row-step touched by one fast iteration
         for (; k + AHEAD * RSTEP < k_end; k += 2 * UNROLL * RSTEP) {
+            group_step(k);
             if constexpr (EAGER) {
                 consume_fast(wa, k);
                 issue_fast(wa, k + 2 * UNROLL * RSTEP);
@@ -190,6 +237,7 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     }
     // guarded remainder (same buffer invariants: wa holds rows k.., and for EAGER wb holds rows k + UNROLL*RSTEP..)
     for (; k < k_end; k += 2 * UNROLL * RSTEP) {
+        group_step(k);
         if constexpr (EAGER) {
             consume(wa, k);
             issue(wa, k + 2 * UNROLL * RSTEP);
@@ -201,6 +249,12 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
             issue(wa, k + 2 * UNROLL * RSTEP);
             consume(wb, k + UNROLL * RSTEP);
         }
+    }
+
+    if constexpr (GROUPED) {
+        fold(cur_g);
+#pragma unroll
+        for (int j = 0; j < COLS; ++j) acc[0][j] = tot[j];
     }
 
     // rows-in-warp -> one partial per column (lanes lir, lir+LPR, ... hold the same columns)

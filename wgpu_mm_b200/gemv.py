@@ -12,3 +12,4 @@ def insert_matrix_dims(context: dict, dims=None):
 
 
 qgemv_1, qgemv_sint8, gemv_f32 = (_entry(n) for n in ("qgemv_1", "qgemv_sint8", "gemv_f32"))
+qgemv_sint8_grouped = _entry("qgemv_sint8_grouped")  # per-group scales, group_k = 128
