@@ -289,11 +289,12 @@ def run_single(args):
         # ---------------- GEMV fp32 1x4096 * 4096x16384: 4 weight sets = 1 GiB rotated (> L2) ----------------
         Kv, Nv = 4096, 16384
         gsets = make_sets(ctx, 1, Nv, Kv, 4, 300)
-        kg = ctx.kernel(w.KernelId.GEMV_F32, 1, Nv, Kv, w.KernelParams(tune=(args.gemv_variant, 0, 0, 0)))
+        AT = int(w.Flags.AUTOTUNE)  # geometry / K-split count measured once at kernel creation (no-op when --gemv-variant is given)
+        kg = ctx.kernel(w.KernelId.GEMV_F32, 1, Nv, Kv, w.KernelParams(tune=(args.gemv_variant, 0, 0, 0), flags=AT))
         ms = time_back_to_back(ctx, kg, gsets, 200, 20)
         tot = ms * 40
         gbytes = 4.0 * Kv * Nv + 4 * Kv + 4 * Nv
-        extras["gemv_f32_4096x16384"] = {"gbps": gbytes / (ms * 1e-3) / 1e9, "kernel_us": ms * 1e3, "timing": "200 back-to-back PDL launches, 4 weight sets (1 GiB) rotated",
+        extras["gemv_f32_4096x16384"] = {"gbps": gbytes / (ms * 1e-3) / 1e9, "kernel_us": ms * 1e3, "geometry": list(kg.geometry()), "timing": "200 back-to-back PDL launches, 4 weight sets (1 GiB) rotated",
                                          "roofline": {"bound": "hbm", "achieved": gbytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                                       "frac": gbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic.get("gemv_stream_kernel<GemvF32>@4096x16384"),
                                                       "algorithmic_bytes": gbytes, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['_source']})"}}
@@ -301,11 +302,11 @@ def run_single(args):
         # ---------------- qGEMV sint8 1x4096 * 4096x14336: 8 weight sets = 470 MB rotated (> L2) ----------------
         Kq, Nq = 4096, 14336
         qsets = make_sets(ctx, 1, Nq, Kq, 8, 500, quant=True)
-        kq = ctx.kernel(w.KernelId.QGEMV_SINT8, 1, Nq, Kq, w.KernelParams(absmax=2.0, batch=1, tune=(args.gemv_variant, 0, 0, 0)))
+        kq = ctx.kernel(w.KernelId.QGEMV_SINT8, 1, Nq, Kq, w.KernelParams(absmax=2.0, batch=1, tune=(args.gemv_variant, 0, 0, 0), flags=AT))
         ms = time_back_to_back(ctx, kq, qsets, 400, 40)
         tot = ms * 80
         qbytes = 1.0 * Kq * Nq + 4 * Kq + 4 * Nq
-        extras["qgemv_sint8_4096x14336"] = {"gbps": qbytes / (ms * 1e-3) / 1e9, "kernel_us": ms * 1e3, "timing": "400 back-to-back PDL launches, 8 weight sets (470 MB) rotated",
+        extras["qgemv_sint8_4096x14336"] = {"gbps": qbytes / (ms * 1e-3) / 1e9, "kernel_us": ms * 1e3, "geometry": list(kq.geometry()), "timing": "400 back-to-back PDL launches, 8 weight sets (470 MB) rotated",
                                             "roofline": {"bound": "hbm", "achieved": qbytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                                          "frac": qbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic.get("gemv_stream_kernel<GemvS8>@4096x14336"),
                                                          "algorithmic_bytes": qbytes, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['_source']})"}}
@@ -313,10 +314,10 @@ def run_single(args):
         # ---------------- same shape with per-group scales (group_k = 128): weights + 1.8 MB of scales ----------------
         gk = 128
         qsets = make_sets(ctx, 1, Nq, Kq, 8, 600, quant=True, group_k=gk)
-        kq = ctx.kernel(w.KernelId.QGEMV_SINT8, 1, Nq, Kq, w.KernelParams(batch=1, group_k=gk))
+        kq = ctx.kernel(w.KernelId.QGEMV_SINT8, 1, Nq, Kq, w.KernelParams(batch=1, group_k=gk, flags=AT))
         ms = time_back_to_back(ctx, kq, qsets, 400, 40)
         gqbytes = qbytes + 4.0 * (Kq // gk) * Nq
-        extras["qgemv_sint8_g128_4096x14336"] = {"gbps": gqbytes / (ms * 1e-3) / 1e9, "kernel_us": ms * 1e3, "algorithmic_bytes": gqbytes,
+        extras["qgemv_sint8_g128_4096x14336"] = {"gbps": gqbytes / (ms * 1e-3) / 1e9, "kernel_us": ms * 1e3, "algorithmic_bytes": gqbytes, "geometry": list(kq.geometry()),
                                                  "frac_of_hbm_peak": gqbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                                  "timing": "400 back-to-back PDL launches, 8 weight sets rotated"}
         kq.free(); free_sets(qsets)

@@ -90,6 +90,10 @@ typedef struct b200mm_kernel_params {
 #define B200MM_F_NONE 0u
 #define B200MM_F_TC3X_1X 0x1u       /* SGEMM_TC3X: single-pass TF32 (fails the reference gate; for ncu/accuracy tables only) */
 #define B200MM_F_SEQUENTIAL_K 0x4u   /* SGEMM_SIMT: never split K across CTAs: every output is one k-sequential fma chain (gemm_5.wgsl order, bit-exact vs its restatement) */
+#define B200MM_F_AUTOTUNE 0x8u      /* GEMV_F32 / QGEMV_SINT8 (M == 1, tune[0] == tune[1] == 0): b200mm_kernel_get times the candidate
+                                     * (geometry, K-split count) pairs once on scratch weights larger than L2 and keeps the fastest.  The
+                                     * shape is baked into the kernel object as in the reference (src/gemm.rs:5-7), so this is the analogue
+                                     * of picking the WGSL tile constants per shape; the result is deterministic per kernel OBJECT. */
 #define B200MM_F_PEER_STORE 0x2u    /* SGEMM_*: epilogue also stores the C panel to the peers set by b200mm_kernel_set_peers   */
 
 typedef struct b200mm_ctx b200mm_ctx;

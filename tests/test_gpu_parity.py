@@ -197,7 +197,7 @@ def test_gemv_f32_split_k_is_deterministic(gpu_ctx, oracle, splits, cluster_off)
 QSHAPES = [(1024, 1024), (64, 64), (4096, 14336), (200, 48), (36, 16)]
 
 
-@pytest.mark.parametrize("variant", [0, 100, 1, 5, 6])
+@pytest.mark.parametrize("variant", [0, 100, 1, 4, 5, 6, 11, 12, 16])
 @pytest.mark.parametrize("kn", QSHAPES)
 def test_qgemv_sint8(gpu_ctx, oracle, kn, variant):
     """Quantised GEMV in the src/quant.rs format with the reference's ABSMAX = 2.0 quirk."""
@@ -327,6 +327,45 @@ def test_qgemv_grouped_batched_and_errors(gpu_ctx, oracle):
     dC = gpu_ctx.buffer_from(np.zeros(N, dtype=np.float32))
     with pytest.raises(w.B200mmError):
         gpu_ctx.launch(kern, dA, dB, dC)
+    for b in (dA, dB, dC):
+        b.free()
+    kern.free()
+
+
+@pytest.mark.parametrize("case", [("f32", 1024, 2048, 0), ("s8", 4096, 14336, 0), ("s8", 1024, 1024, 128), ("s8", 200, 48, 0)])
+def test_gemv_autotune_keeps_parity(gpu_ctx, oracle, case):
+    """B200MM_F_AUTOTUNE picks the geometry / K-split count by measurement at kernel creation; whatever it picks must
+    pass the same gates, launch after launch (the choice is fixed per kernel object)."""
+    import wgpu_mm_b200 as w
+    from wgpu_mm_b200.quant import sint8_quantize_grouped, split_grouped
+    kind, K, N, G = case
+    x = oracle.generate_weight_data(81, 1, K)
+    W = oracle.generate_weight_data(82, K, N)
+    flags = int(w.Flags.AUTOTUNE)
+    before = gpu_ctx.launch_count
+    if kind == "f32":
+        kern = gpu_ctx.kernel(w.KernelId.GEMV_F32, 1, N, K, w.KernelParams(flags=flags))
+        B, want64 = W, oracle.mm_f64(x, W)
+    elif G:
+        kern = gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 1, N, K, w.KernelParams(flags=flags, group_k=G))
+        B = sint8_quantize_grouped(W, K, N, G)
+        words, scales = split_grouped(B, K, N, G)
+        want64 = oracle.qgemv_grouped_f64(x, words, scales, 1, N, K, G)
+    else:
+        kern = gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 1, N, K, w.KernelParams(flags=flags, absmax=2.0))
+        B, _ = oracle.sint8_quantize(W, K, N)
+        want64 = oracle.qgemv_f64(x, B, 1, N, K, 2.0)
+    assert gpu_ctx.launch_count == before  # tuning launches are not counted as user launches
+    dA, dB, dC = gpu_ctx.buffer_from(x), gpu_ctx.buffer_from(np.ascontiguousarray(B)), gpu_ctx.buffer_from(np.full(N, 7.5, dtype=np.float32))
+    outs = []
+    for _ in range(3):
+        gpu_ctx.launch(kern, dA, dB, dC)
+        outs.append(dC.read(np.float32).reshape(1, N))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    e, m = oracle.err_vs_f64(outs[0], want64)
+    assert e / m <= REL_F64, f"rel err vs fp64 {e / m:.3e}"
+    grid, block = kern.geometry()
+    assert 1 <= grid[1] <= 8
     for b in (dA, dB, dC):
         b.free()
     kern.free()

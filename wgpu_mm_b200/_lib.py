@@ -43,6 +43,7 @@ class Flags(enum.IntFlag):
     TC3X_1X = 0x1
     PEER_STORE = 0x2
     SEQUENTIAL_K = 0x4
+    AUTOTUNE = 0x8
 
 
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_LIMITS, ERR_UNSUPPORTED, ERR_TOLERANCE = -1, -2, -3, -4, -5, -6

@@ -406,8 +406,29 @@ static void gemv_pick(int variant, void (**fn)(const float*, const void*, float*
                       int* warps, int* lpr, int mrows = 1, bool grouped = false) {
     if constexpr (T::COLS == 16) {
         if (grouped) {  // per-group scales: the default sint8 geometry only (window = 2 * 4 * 16 = 128 rows)
-            *fn = gemv_stream_kernel<T, 8, 4, 16, 1, true>;
+            // default: 3 CTAs/SM (79 registers, no spills; 17.0 us at cfg4); 12: 2 CTAs/SM (18.0 us); 14: 4 CTAs/SM (spills, 19.6 us)
+            *fn = variant == 14 ? gemv_stream_kernel<T, 8, 4, 16, 1, true, 4> : variant == 12 ? gemv_stream_kernel<T, 8, 4, 16, 1, true, 2> : gemv_stream_kernel<T, 8, 4, 16, 1, true, 3>;
             *warps = 8;
+            *lpr = 16;
+            return;
+        }
+    }
+    if constexpr (T::COLS == 16) {
+        if (mrows == 1 && (variant == 11 || variant == 12)) {  // experiment: default geometry at 3 / 4 CTAs per SM
+            *fn = variant == 11 ? gemv_stream_kernel<T, 8, 4, 16, 1, false, 3> : gemv_stream_kernel<T, 8, 4, 16, 1, false, 4>;
+            *warps = 8;
+            *lpr = 16;
+            return;
+        }
+        if (mrows == 1 && variant >= 13 && variant <= 15) {  // experiment: both register buffers in flight before the PDL wait
+            *fn = variant == 13 ? gemv_stream_kernel<T, 8, 4, 16, 1, false, 1, 1> : variant == 14 ? gemv_stream_kernel<T, 8, 4, 16, 1, false, 2, 1> : gemv_stream_kernel<T, 8, 4, 16, 1, false, 3, 1>;
+            *warps = 8;
+            *lpr = 16;
+            return;
+        }
+        if (mrows == 1 && variant >= 16 && variant <= 18) {  // experiment: 4 warps (128 threads), same panel
+            *fn = variant == 16 ? gemv_stream_kernel<T, 4, 4, 16, 1, false, 4> : variant == 17 ? gemv_stream_kernel<T, 4, 4, 16, 1, false, 6> : gemv_stream_kernel<T, 4, 4, 16, 1, false, 4, 1>;
+            *warps = 4;
             *lpr = 16;
             return;
         }
@@ -658,7 +679,8 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
         return fail(ctx, B200MM_ERR_INVALID, "%s needs N%%%d==0 and K%%4==0", b200mm_kernel_name(k->id), cols);
     if (N > INT32_MAX || K > INT32_MAX) return fail(ctx, B200MM_ERR_INVALID, "shape too large");
     // tune[0]: 0 = default for the weight type (measured on B200, tools/sweep_gemv.py), 100 = variant 0, else the variant id
-    k->gemv_variant = k->prm.tune[0] == 0 ? (quant ? 4 : 5) : (k->prm.tune[0] == 100 ? 0 : (int)k->prm.tune[0]);
+    // sint8 default = 13: the 8-warp / 256-column geometry of variant 4 with both register buffers in flight (12.75 vs 13.45 us at cfg4)
+    k->gemv_variant = k->prm.tune[0] == 0 ? (quant ? 13 : 5) : (k->prm.tune[0] == 100 ? 0 : (int)k->prm.tune[0]);
     void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t, PeerStore, int, int);
     int warps, lpr;
     const size_t group_k = k->prm.group_k;
@@ -688,6 +710,13 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
         const size_t slots = (size_t)ctx->prop.multiProcessorCount * occ;
         splits = (int)(slots / ((size_t)k->panels * batch));
         splits = std::max(1, std::min(splits, 64));
+        if (quant && !group_k && mrows == 1) {
+            // sint8 at 2 CTAs/SM: a power-of-two count keeps the K-splits equal (no guarded remainder) and leaves CTA slots free
+            // for the next programmatic-dependent launch to become resident and prefetch (cfg4: 4 splits 12.75 us, 5 splits 18.2 us)
+            int p2 = 1;
+            while (p2 * 2 <= splits) p2 *= 2;
+            splits = p2;
+        }
         splits = (int)std::min<size_t>(splits, std::max<size_t>(1, K / 32));
     }
     // K-splits of a panel are reduced inside a thread-block cluster (<= 8 CTAs, portable size) unless tune[3] == 1
@@ -700,15 +729,47 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
             splits = 8;
     }
     const int rstep = group_k ? 128 : warps * (32 / lpr);  // grouped: splits start on a pipeline-window boundary
-    size_t rps = ceil_div(K, (size_t)splits);
-    rps = ceil_div(rps, rstep) * rstep;
+    auto smem_for = [&](size_t rows) {
+        size_t b = ((size_t)mrows * rows + (size_t)warps * mrows * panel + (size_t)mrows * panel) * sizeof(float);
+        if (group_k) b += ((rows / group_k + 2) * panel + (size_t)warps * 32 * cols) * sizeof(float);  // scales + per-thread totals
+        return b;
+    };
+    auto rows_for = [&](int sp) { return ceil_div(ceil_div(K, (size_t)sp), (size_t)rstep) * rstep; };
+    if (k->gemv_cluster && k->prm.tune[1] == 0 && splits > 1) {
+        // A cluster lives inside one GPC, so "CTAs <= SMs x occupancy" does not guarantee that all clusters are co-resident
+        // (measured at cfg4: 56 clusters of 5 at 2 CTAs/SM spill into a second wave, 18.2 us instead of 12.8 us with 4).
+        // Ask the driver how many clusters of each size fit and take the largest split count that stays in one wave.
+        const bool dbg = getenv("B200MM_DEBUG_GEMV") != nullptr;
+        for (; splits > 1; --splits) {
+            const size_t rows = rows_for(splits);
+            const int sp = (int)ceil_div(K, rows);
+            const size_t smem = smem_for(rows);
+            if (smem > 200 * 1024) continue;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(k->panels, sp, batch);
+            cfg.blockDim = dim3(warps * 32, 1, 1);
+            cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 1;
+            attr[0].val.clusterDim.y = (unsigned)sp;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int max_clusters = 0;
+            CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+            CU_TRY(ctx, cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg));
+            if (dbg) fprintf(stderr, "[b200mm] gemv %zux%zu variant %d: clusters of %d -> %d co-resident (need %zu)\n", K, N, k->gemv_variant, sp, max_clusters, (size_t)k->panels * batch);
+            if ((size_t)max_clusters >= (size_t)k->panels * batch) break;
+        }
+    }
+    size_t rps = rows_for(splits);
     splits = (int)ceil_div(K, rps);
     k->splits = splits;
     k->rows_per_split = (int)rps;
     k->grid = dim3(k->panels, splits, batch);
     k->block = dim3(warps * 32, 1, 1);
-    k->smem = ((size_t)mrows * rps + (size_t)warps * mrows * panel + (size_t)mrows * panel) * sizeof(float);
-    if (group_k) k->smem += (rps / group_k + 2) * panel * sizeof(float);
+    k->smem = smem_for(rps);
     if (k->smem > 200 * 1024) return fail(ctx, B200MM_ERR_INVALID, "gemv: K-split too long for shared memory");
     CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(k->smem, 48 * 1024)));
     if (splits > 1 && !k->gemv_cluster) {
@@ -720,6 +781,90 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
         k->tickets = (unsigned int*)((char*)k->ws + ceil_div(pbytes, 256) * 256);
         CU_TRY(ctx, cudaMemsetAsync(k->ws, 0, k->ws_bytes, ctx->stream));
     }
+    return B200MM_OK;
+}
+
+// B200MM_F_AUTOTUNE: the best (instantiation, K-split count) of the streaming GEMV depends on how whole clusters pack into
+// GPCs and on how much room the NEXT programmatic-dependent launch finds to become resident early -- at cfg4 neighbouring
+// split counts differ by 40 % and no occupancy formula predicts the order.  So measure: every candidate is timed with
+// back-to-back launches over scratch weight sets that together exceed L2, and the fastest one is kept.
+static int gemv_autotune(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
+    const size_t K = k->K, N = k->N;
+    const size_t batch = k->prm.batch ? k->prm.batch : 1;
+    const size_t group_k = k->prm.group_k;
+    const size_t wbytes = batch * (quant ? K * N + (group_k ? ceil_div(K, group_k) * N * 4 : 0) : K * N * 4);
+    const int nsets = (int)std::max<size_t>(2, std::min<size_t>(8, ceil_div((size_t)320 << 20, wbytes)));
+    char* W = nullptr;
+    float *x = nullptr, *y = nullptr;
+    CU_TRY(ctx, cudaMalloc(&W, wbytes * nsets));
+    CU_TRY(ctx, cudaMalloc(&x, batch * K * sizeof(float)));
+    CU_TRY(ctx, cudaMalloc(&y, batch * N * sizeof(float)));
+    CU_TRY(ctx, cudaMemsetAsync(W, 0x11, wbytes * nsets, ctx->stream));  // any byte pattern is a valid int8 / finite f32 weight
+    CU_TRY(ctx, cudaMemsetAsync(x, 0, batch * K * sizeof(float), ctx->stream));
+    cudaEvent_t e0, e1;
+    CU_TRY(ctx, cudaEventCreate(&e0));
+    CU_TRY(ctx, cudaEventCreate(&e1));
+    static const int f32_variants[] = {5, 100, 2, 3};
+    static const int s8_variants[] = {4, 11, 12, 13};
+    static const int s8g_variants[] = {4, 12, 14};
+    const int* variants = quant ? (group_k ? s8g_variants : s8_variants) : f32_variants;
+    const int nvar = quant ? (group_k ? 3 : 4) : 4;
+    const uint64_t launches_before = ctx->launches;
+    float best_ms = 1e30f;
+    uint32_t best_v = 0, best_s = 0;
+    const bool dbg = getenv("B200MM_DEBUG_GEMV") != nullptr;
+    int rc = B200MM_OK;
+    for (int vi = 0; vi < nvar && rc == B200MM_OK; ++vi)
+        for (uint32_t sp = 1; sp <= 8 && rc == B200MM_OK; ++sp) {
+            if (sp > K / 32 && sp > 1) break;
+            b200mm_kernel t;
+            t.id = k->id;
+            t.M = 1;
+            t.N = N;
+            t.K = K;
+            t.prm = k->prm;
+            t.prm.flags &= ~(B200MM_F_AUTOTUNE | B200MM_F_PEER_STORE);
+            t.prm.tune[0] = (uint32_t)variants[vi];
+            t.prm.tune[1] = sp;
+            if (setup_gemv(ctx, &t, quant) != B200MM_OK) continue;  // e.g. the split does not fit shared memory
+            if ((uint32_t)t.splits != sp) {                         // rounding merged it into a smaller count: already timed
+                if (t.ws) cudaFree(t.ws);
+                continue;
+            }
+            const int reps = 24;
+            float ms = 1e30f;
+            for (int round = 0; round < 3 && rc == B200MM_OK; ++round) {
+                if (round) cudaEventRecord(e0, ctx->stream);
+                for (int i = 0; i < reps && rc == B200MM_OK; ++i) rc = b200mm_launch_ptr(ctx, &t, x, W + (size_t)(i % nsets) * wbytes, y, nullptr);
+                if (round) {
+                    cudaEventRecord(e1, ctx->stream);
+                    if (cudaEventSynchronize(e1) != cudaSuccess) rc = fail(ctx, B200MM_ERR_CUDA, "gemv autotune: %s", cudaGetErrorString(cudaGetLastError()));
+                    float m = 0.f;
+                    cudaEventElapsedTime(&m, e0, e1);
+                    ms = std::min(ms, m / reps);
+                }
+            }
+            if (dbg) fprintf(stderr, "[b200mm] autotune %zux%zu variant %d splits %u: %.2f us\n", K, N, variants[vi], sp, ms * 1e3f);
+            if (rc == B200MM_OK && ms < best_ms) {
+                best_ms = ms;
+                best_v = (uint32_t)variants[vi];
+                best_s = sp;
+            }
+            cudaStreamSynchronize(ctx->stream);
+            if (t.ws) cudaFree(t.ws);
+        }
+    cudaStreamSynchronize(ctx->stream);
+    ctx->launches = launches_before;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(W);
+    cudaFree(x);
+    cudaFree(y);
+    if (rc != B200MM_OK) return rc;
+    if (best_s == 0) return fail(ctx, B200MM_ERR_INVALID, "gemv autotune: no candidate geometry fits");
+    k->prm.tune[0] = best_v;
+    k->prm.tune[1] = best_s;
+    if (dbg) fprintf(stderr, "[b200mm] autotune %zux%zu -> variant %u, %u splits, %.2f us\n", K, N, best_v, best_s, best_ms * 1e3f);
     return B200MM_OK;
 }
 
@@ -742,10 +887,19 @@ extern "C" int b200mm_kernel_get(b200mm_ctx* ctx, int kernel_id, size_t M, size_
         rc = setup_simt(ctx, k);
     else if (kernel_id == B200MM_K_SGEMM_TC3X)
         rc = setup_tc3x(ctx, k);
-    else if (kernel_id == B200MM_K_GEMV_F32)
-        rc = setup_gemv(ctx, k, false);
-    else if (kernel_id == B200MM_K_QGEMV_SINT8)
-        rc = setup_gemv(ctx, k, true);
+    else if (kernel_id == B200MM_K_GEMV_F32 || kernel_id == B200MM_K_QGEMV_SINT8) {
+        const bool quant = kernel_id == B200MM_K_QGEMV_SINT8;
+        rc = setup_gemv(ctx, k, quant);  // validates the shape; also the result when no tuning is asked for
+        if (rc == B200MM_OK && (k->prm.flags & B200MM_F_AUTOTUNE) && M == 1 && k->prm.tune[0] == 0 && k->prm.tune[1] == 0) {
+            if (k->ws) cudaFree(k->ws);
+            k->ws = nullptr;
+            k->ws_bytes = 0;
+            k->partial = nullptr;
+            k->tickets = nullptr;
+            rc = gemv_autotune(ctx, k, quant);
+            if (rc == B200MM_OK) rc = setup_gemv(ctx, k, quant);
+        }
+    }
     else
         rc = fail(ctx, B200MM_ERR_UNSUPPORTED, "unknown kernel id %d", kernel_id);
     if (rc) {

@@ -95,8 +95,8 @@ __device__ __forceinline__ void store_y(float* y, int gc, float v, const PeerSto
 //   partial dot product of a group is folded into the running total with ONE fma per column when the group changes, so
 //   the inner loop is the ungrouped one.  The CTA's scales (<= rows_per_split/group_k + 1 groups x PANEL columns) are
 //   staged in shared memory up front, off the critical path.
-template <class T, int WARPS, int UNROLL, int LPR, int MROWS = 1, bool GROUPED = false>
-__global__ void __launch_bounds__(WARPS * 32, GROUPED ? 3 : 1)
+template <class T, int WARPS, int UNROLL, int LPR, int MROWS = 1, bool GROUPED = false, int MINB = 1, int EAGER_ = -1>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, float* __restrict__ y,
                    float* __restrict__ partial, unsigned int* __restrict__ tickets, int K, int N, int rows_per_split,
                    float out_scale, size_t x_batch_stride, size_t w_batch_stride_bytes, size_t y_batch_stride,
@@ -142,7 +142,7 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     };
     // fp32: both register buffers are in flight before anything dependent is touched (58.7 MB shape: 12.8 -> 10.7 us).
     // sint8 keeps one (the longer live ranges cost it an occupancy step: measured 15.6 -> 19 us with both).
-    constexpr bool EAGER = (T::COLS == 4);
+    constexpr bool EAGER = EAGER_ < 0 ? (T::COLS == 4) : (EAGER_ != 0);
     issue(wa, k);
     if constexpr (EAGER) issue(wb, k + UNROLL * RSTEP);
     // grouped scales of this CTA's rows x columns -> shared memory (weights: independent of the previous kernel)
@@ -169,21 +169,28 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     for (int m = 0; m < MROWS; ++m)
 #pragma unroll
         for (int j = 0; j < COLS; ++j) acc[m][j] = 0.f;
-    // GROUPED: acc[0] is the current group's partial, tot the scaled running total
-    float tot[GROUPED ? COLS : 1];
+    // GROUPED: acc[0] is the current group's partial; the scaled running total lives in shared memory ([j/4][thread] float4
+    // slots, conflict-free) so that the streaming loop keeps the register budget -- and the occupancy -- of the ungrouped kernel.
+    float4* tot4 = reinterpret_cast<float4*>(ss + ngl * PANEL);
     int cur_g = 0;
     if constexpr (GROUPED) {
 #pragma unroll
-        for (int j = 0; j < COLS; ++j) tot[j] = 0.f;
+        for (int j = 0; j < COLS / 4; ++j) tot4[j * (WARPS * 32) + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
         cur_g = k / group_k;
     }
     auto fold = [&](int g) {
         if constexpr (GROUPED) {
-            const float* s = ss + min(max(g - g0, 0), ngl - 1) * PANEL + lir * COLS;
+            const float4* s4 = reinterpret_cast<const float4*>(ss + min(max(g - g0, 0), ngl - 1) * PANEL + lir * COLS);
 #pragma unroll
-            for (int j = 0; j < COLS; ++j) {
-                tot[j] = fmaf(acc[0][j], s[j], tot[j]);
-                acc[0][j] = 0.f;
+            for (int j = 0; j < COLS / 4; ++j) {
+                float4 t = tot4[j * (WARPS * 32) + tid];
+                const float4 sc = s4[j];
+                t.x = fmaf(acc[0][4 * j + 0], sc.x, t.x);
+                t.y = fmaf(acc[0][4 * j + 1], sc.y, t.y);
+                t.z = fmaf(acc[0][4 * j + 2], sc.z, t.z);
+                t.w = fmaf(acc[0][4 * j + 3], sc.w, t.w);
+                tot4[j * (WARPS * 32) + tid] = t;
+                acc[0][4 * j + 0] = acc[0][4 * j + 1] = acc[0][4 * j + 2] = acc[0][4 * j + 3] = 0.f;
             }
         }
     };
@@ -254,7 +261,13 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     if constexpr (GROUPED) {
         fold(cur_g);
 #pragma unroll
-        for (int j = 0; j < COLS; ++j) acc[0][j] = tot[j];
+        for (int j = 0; j < COLS / 4; ++j) {
+            const float4 t = tot4[j * (WARPS * 32) + tid];
+            acc[0][4 * j + 0] = t.x;
+            acc[0][4 * j + 1] = t.y;
+            acc[0][4 * j + 2] = t.z;
+            acc[0][4 * j + 3] = t.w;
+        }
     }
 
     // rows-in-warp -> one partial per column (lanes lir, lir+LPR, ... hold the same columns)
