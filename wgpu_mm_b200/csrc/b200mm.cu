@@ -1116,6 +1116,7 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
             const float scale = quant ? (group_k ? 1.0f : k->prm.absmax) / 127.0f : 1.0f;
             const size_t wstride = quant ? (size_t)K * N + (group_k ? ceil_div(K, group_k) * N * 4 : 0) : (size_t)K * N * 4;
             if (k->peers.world && (k->prm.batch > 1 || k->M > 1)) return fail(ctx, B200MM_ERR_INVALID, "peer stores are not supported for batched / multi-row GEMV");
+            if (((uintptr_t)A | (uintptr_t)B) & 15) return fail(ctx, B200MM_ERR_INVALID, "gemv: x and W must be 16-byte aligned (128-bit loads)");
             // launched with programmatic stream serialization (PDL): see the griddepcontrol comments in gemv.cuh
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = k->grid;

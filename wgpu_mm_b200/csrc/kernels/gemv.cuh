@@ -159,9 +159,15 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
+    // x -> shared memory with 128-bit loads (K % 4 == 0, splits start on multiples of 4): this sits between the PDL wait and the
+    // first FMA, so a scalar strided loop (rows_per_split / threads dependent L2 round trips) was ~1 us of a ~12 us kernel
 #pragma unroll
-    for (int m = 0; m < MROWS; ++m)
-        for (int i = tid; i < rows_per_split; i += WARPS * 32) xs[m * rows_per_split + i] = (k_beg + i < k_end) ? x[(size_t)m * K + k_beg + i] : 0.f;
+    for (int m = 0; m < MROWS; ++m) {
+        const float4* xg = reinterpret_cast<const float4*>(x + (size_t)m * K + k_beg);
+        float4* xs4 = reinterpret_cast<float4*>(xs + m * rows_per_split);
+        const int n4 = rows_per_split >> 2, valid4 = (k_end - k_beg) >> 2;  // k_end - k_beg is a multiple of 4
+        for (int i = tid; i < n4; i += WARPS * 32) xs4[i] = i < valid4 ? __ldg(xg + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     __syncthreads();
 
     float acc[MROWS][COLS];
@@ -306,14 +312,21 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
             const uint32_t local = smem_u32(cta_part);
             for (int c = tid; c < MROWS * PANEL; c += WARPS * 32) {
                 const int m = c / PANEL, gc = panel * PANEL + c % PANEL;
-                float s = 0.f;
-                for (int r = 0; r < splits; ++r) {
-                    uint32_t remote;
-                    float v;
-                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local + 4u * c), "r"(r));
-                    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
-                    s += v;
+                // all remote reads first (<= 8 splits in a cluster), then the fixed-order sum: one DSMEM latency instead of `splits`
+                float v[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    v[r] = 0.f;
+                    if (r < splits) {
+                        uint32_t remote;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local + 4u * c), "r"(r));
+                        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v[r]) : "r"(remote) : "memory");
+                    }
                 }
+                float s = 0.f;
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (r < splits) s += v[r];
                 if (gc < N) store_y(y + (size_t)m * N, gc, s * out_scale, peers);
             }
         }
