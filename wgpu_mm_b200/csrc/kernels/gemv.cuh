@@ -200,12 +200,15 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
             }
         }
     };
-    auto group_step = [&](int kk) {  // entering the window whose first row (for this thread) is kk: warp-uniform branch
+    // entering the window whose first row (for this thread) is kk: warp-uniform branch.  Windows advance by 128 rows <= group_k,
+    // so at most one group boundary is crossed per step and a compare against the next boundary replaces the division.
+    int next_boundary = GROUPED ? (cur_g + 1) * group_k : 0;
+    auto group_step = [&](int kk) {
         if constexpr (GROUPED) {
-            const int g = kk / group_k;
-            if (g != cur_g) {
+            if (kk >= next_boundary) {
                 fold(cur_g);
-                cur_g = g;
+                ++cur_g;
+                next_boundary += group_k;
             }
         }
     };
