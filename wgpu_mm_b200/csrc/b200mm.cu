@@ -623,7 +623,18 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     const size_t tiles_all = ceil_div(M, 128) * ceil_div(N, k->tc_bn);
     const int sms = ctx->prop.multiProcessorCount;
     // hybrid schedule: whole-tile waves while there are >= one tile per SM, stream-K over the remainder
-    const int grid_x = (int)std::min<long long>((long long)tiles_all * k->tc_cpt, sms);
+    int grid_x = (int)std::min<long long>((long long)tiles_all * k->tc_cpt, sms);
+    if ((long long)tiles_all < sms && k->prm.tune[1] != 1) {
+        // Fewer tiles than SMs (skinny M, and the row panels of the pipelined host-buffer path): plain stream-K gives every CTA a
+        // k-range that starts somewhere else, so CTAs that share an A row panel or a B column panel are never at the same k and
+        // nothing is reused out of L2 -- ncu at 1024 x 4096 x 4096: 966 MB of DRAM reads for 176 MB of operands, DRAM-bound.
+        // Instead split every tile into the same S k-slices (S | chains per tile, tiles x S <= SMs): one segment per CTA, all
+        // CTAs walk k in lock-step, and CTA b and b + S read the same k-slice of neighbouring tiles at the same time.
+        int S = 1;
+        for (int d = 1; d <= k->tc_cpt; ++d)
+            if (k->tc_cpt % d == 0 && (long long)tiles_all * d <= sms) S = d;
+        grid_x = (int)tiles_all * S;
+    }
     k->tc_full_waves = (int)(tiles_all / grid_x);
     if (k->prm.tune[1] == 1) k->tc_full_waves = 0;  // tune[1] = 1: pure stream-K (for experiments)
     k->tc_sk_units = (long long)(tiles_all - (size_t)k->tc_full_waves * grid_x) * k->tc_cpt;
