@@ -9,7 +9,7 @@ import bench
 ctx = w.Context(0)
 K, N = 4096, 14336
 gks = [int(a) for a in sys.argv[1:]] or [0]
-variants = [int(v) for v in os.environ.get("VARIANTS", "0,11,12,13,14,15,16,17,18,1,6,7").split(",")]
+variants = [int(v) for v in os.environ.get("VARIANTS", "0,4,11,12,1,6,7").split(",")]
 for gk in gks:
     sets = bench.make_sets(ctx, 1, N, K, 8, 600, quant=True, group_k=gk)
     for variant in variants:

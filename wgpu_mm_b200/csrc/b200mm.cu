@@ -399,87 +399,57 @@ using Tc256k16 = Tc3xCfg<256, 4, false, 16>;  // 4 stages x 48 KB: same bytes in
 using Tc128 = Tc3xCfg<128, 3, false, 32>;
 using Tc256x1 = Tc3xCfg<256, 4, true, 32>;
 
-// gemv variants: 0: 8 warps, unroll 8, full-warp rows;  1: 8 warps, unroll 8, half-warp rows
+// Streaming-GEMV instantiations (template arguments: warps, unroll, lanes per row segment, rows of x, grouped scales,
+// min CTAs/SM, eager double prefetch).  Variant ids are what params.tune[0] / the autotuner select; measured at cfg3 / cfg4
+// with tools/sweep_gemv.py and tools/bench_grouped.py (profiles/r1_qgemv_variant_split_sweep.log).
+//   0 (tune 100)  8 warps, unroll 8, 32 lanes/row        4  8 warps, unroll 4, 16 lanes/row (sint8 default until the eager form)
+//   1             8 warps, unroll 8, 16 lanes/row        5  4 warps, unroll 4, 32 lanes/row (fp32 default)
+//   2             4 warps, unroll 8, 32 lanes/row        6  4 warps, unroll 8, 16 lanes/row
+//   3             8 warps, unroll 4, 32 lanes/row        7  4 warps, unroll 4, 16 lanes/row
+//   sint8 only: 11 = variant 4 capped at 80 registers (3 CTAs/SM), 12 = at 64 registers (4 CTAs/SM),
+//               13 = variant 4 with both register buffers in flight before the PDL wait (128 registers, 2 CTAs/SM; the default)
+//   sint8 with per-group scales (8 warps, unroll 4, 16 lanes: window of 128 rows): default = eager, 2 CTAs/SM; 11 = 3 CTAs/SM;
+//               12 = 2 CTAs/SM without the eager prefetch; 14 = 4 CTAs/SM (spills)
+using GemvFn = void (*)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t, PeerStore, int,
+                        int);
+struct GemvPick {
+    GemvFn fn;
+    int warps, lpr;
+};
+#define GEMV_INST(W, U, L, ...) \
+    GemvPick { gemv_stream_kernel<T, W, U, L, ##__VA_ARGS__>, W, L }
+
 template <class T>
-static void gemv_pick(int variant, void (**fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float,
-                                               size_t, size_t, size_t, PeerStore, int, int),
-                      int* warps, int* lpr, int mrows = 1, bool grouped = false) {
+static GemvPick gemv_pick(int variant, int mrows = 1, bool grouped = false) {
     if constexpr (T::COLS == 16) {
-        if (grouped) {  // per-group scales: the default sint8 geometry only (window = 2 * 4 * 16 = 128 rows)
-            // default: both register buffers in flight, 120 registers, 2 CTAs/SM (15.7 us at cfg4 / group_k 128); 11: 3 CTAs/SM, one
-            // buffer ahead (16.3 us); 12: 2 CTAs/SM, one buffer ahead (16.9 us); 14: 4 CTAs/SM (spills, 19.1 us)
-            *fn = variant == 14 ? gemv_stream_kernel<T, 8, 4, 16, 1, true, 4> : variant == 12 ? gemv_stream_kernel<T, 8, 4, 16, 1, true, 2>
-                : variant == 11 ? gemv_stream_kernel<T, 8, 4, 16, 1, true, 3> : gemv_stream_kernel<T, 8, 4, 16, 1, true, 2, 1>;
-            *warps = 8;
-            *lpr = 16;
-            return;
+        if (grouped) {
+            switch (variant) {
+                case 11: return GEMV_INST(8, 4, 16, 1, true, 3);
+                case 12: return GEMV_INST(8, 4, 16, 1, true, 2);
+                case 14: return GEMV_INST(8, 4, 16, 1, true, 4);
+                default: return GEMV_INST(8, 4, 16, 1, true, 2, 1);
+            }
         }
-    }
-    if constexpr (T::COLS == 16) {
-        if (mrows == 1 && (variant == 11 || variant == 12)) {  // experiment: default geometry at 3 / 4 CTAs per SM
-            *fn = variant == 11 ? gemv_stream_kernel<T, 8, 4, 16, 1, false, 3> : gemv_stream_kernel<T, 8, 4, 16, 1, false, 4>;
-            *warps = 8;
-            *lpr = 16;
-            return;
-        }
-        if (mrows == 1 && variant >= 13 && variant <= 15) {  // experiment: both register buffers in flight before the PDL wait
-            *fn = variant == 13 ? gemv_stream_kernel<T, 8, 4, 16, 1, false, 1, 1> : variant == 14 ? gemv_stream_kernel<T, 8, 4, 16, 1, false, 2, 1> : gemv_stream_kernel<T, 8, 4, 16, 1, false, 3, 1>;
-            *warps = 8;
-            *lpr = 16;
-            return;
-        }
-        if (mrows == 1 && variant >= 16 && variant <= 18) {  // experiment: 4 warps (128 threads), same panel
-            *fn = variant == 16 ? gemv_stream_kernel<T, 4, 4, 16, 1, false, 4> : variant == 17 ? gemv_stream_kernel<T, 4, 4, 16, 1, false, 6> : gemv_stream_kernel<T, 4, 4, 16, 1, false, 4, 1>;
-            *warps = 4;
-            *lpr = 16;
-            return;
-        }
-    }
-    if (mrows > 1) {
-        // skinny GEMM: only the default geometry of each weight type is instantiated for M = 2, 4, 8
-        if constexpr (T::COLS == 4) {
-            *fn = mrows == 2 ? gemv_stream_kernel<T, 4, 4, 32, 2> : mrows == 4 ? gemv_stream_kernel<T, 4, 4, 32, 4> : gemv_stream_kernel<T, 4, 4, 32, 8>;
-            *warps = 4;
-            *lpr = 32;
-        } else {
-            *fn = mrows == 2 ? gemv_stream_kernel<T, 8, 4, 16, 2> : gemv_stream_kernel<T, 8, 4, 16, 4>;
-            *warps = 8;
-            *lpr = 16;
-        }
-        return;
-    }
-    if (variant == 1) {
-        *fn = gemv_stream_kernel<T, 8, 8, 16>;
-        *warps = 8;
-        *lpr = 16;
-    } else if (variant == 2) {
-        *fn = gemv_stream_kernel<T, 4, 8, 32>;
-        *warps = 4;
-        *lpr = 32;
-    } else if (variant == 3) {
-        *fn = gemv_stream_kernel<T, 8, 4, 32>;
-        *warps = 8;
-        *lpr = 32;
-    } else if (variant == 4) {
-        *fn = gemv_stream_kernel<T, 8, 4, 16>;
-        *warps = 8;
-        *lpr = 16;
-    } else if (variant == 5) {
-        *fn = gemv_stream_kernel<T, 4, 4, 32>;
-        *warps = 4;
-        *lpr = 32;
-    } else if (variant == 6) {
-        *fn = gemv_stream_kernel<T, 4, 8, 16>;
-        *warps = 4;
-        *lpr = 16;
-    } else if (variant == 7) {
-        *fn = gemv_stream_kernel<T, 4, 4, 16>;
-        *warps = 4;
-        *lpr = 16;
+        if (mrows == 2) return GEMV_INST(8, 4, 16, 2);
+        if (mrows > 2) return GEMV_INST(8, 4, 16, 4);
+        if (variant == 11) return GEMV_INST(8, 4, 16, 1, false, 3);
+        if (variant == 12) return GEMV_INST(8, 4, 16, 1, false, 4);
+        if (variant == 13) return GEMV_INST(8, 4, 16, 1, false, 1, 1);
     } else {
-        *fn = gemv_stream_kernel<T, 8, 8, 32>;
-        *warps = 8;
-        *lpr = 32;
+        // skinny GEMM: only the default geometry of each weight type is instantiated for M = 2, 4, 8
+        if (mrows == 2) return GEMV_INST(4, 4, 32, 2);
+        if (mrows == 4) return GEMV_INST(4, 4, 32, 4);
+        if (mrows > 4) return GEMV_INST(4, 4, 32, 8);
+    }
+    switch (variant) {
+        case 1: return GEMV_INST(8, 8, 16);
+        case 2: return GEMV_INST(4, 8, 32);
+        case 3: return GEMV_INST(8, 4, 32);
+        case 4: return GEMV_INST(8, 4, 16);
+        case 5: return GEMV_INST(4, 4, 32);
+        case 6: return GEMV_INST(4, 8, 16);
+        case 7: return GEMV_INST(4, 4, 16);
+        default: return GEMV_INST(8, 8, 32);
     }
 }
 
@@ -694,8 +664,6 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     // tune[0]: 0 = default for the weight type (measured on B200, tools/sweep_gemv.py), 100 = variant 0, else the variant id
     // sint8 default = 13: the 8-warp / 256-column geometry of variant 4 with both register buffers in flight (12.75 vs 13.45 us at cfg4)
     k->gemv_variant = k->prm.tune[0] == 0 ? (quant ? 13 : 5) : (k->prm.tune[0] == 100 ? 0 : (int)k->prm.tune[0]);
-    void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t, PeerStore, int, int);
-    int warps, lpr;
     const size_t group_k = k->prm.group_k;
     if (group_k) {  // per-(row block, column) scales stored behind the weights
         if (!quant) return fail(ctx, B200MM_ERR_INVALID, "group_k applies to qgemv_sint8 only");
@@ -703,10 +671,9 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
         if (group_k % 128) return fail(ctx, B200MM_ERR_INVALID, "qgemv_sint8: group_k must be a multiple of 128 (got %zu)", group_k);
         if (k->prm.flags & B200MM_F_PEER_STORE) return fail(ctx, B200MM_ERR_INVALID, "qgemv_sint8 with group_k: peer stores not supported");
     }
-    if (quant)
-        gemv_pick<GemvS8>(k->gemv_variant, &fn, &warps, &lpr, mrows, group_k != 0);
-    else
-        gemv_pick<GemvF32>(k->gemv_variant, &fn, &warps, &lpr, mrows);
+    const GemvPick pick = quant ? gemv_pick<GemvS8>(k->gemv_variant, mrows, group_k != 0) : gemv_pick<GemvF32>(k->gemv_variant, mrows);
+    const GemvFn fn = pick.fn;
+    const int warps = pick.warps, lpr = pick.lpr;
     const int panel = lpr * cols;
     const unsigned batch = k->prm.batch ? k->prm.batch : 1;
     k->panels = (int)ceil_div(N, panel);
@@ -1131,12 +1098,7 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
         case B200MM_K_GEMV_F32:
         case B200MM_K_QGEMV_SINT8: {
             const bool quant = k->id == B200MM_K_QGEMV_SINT8;
-            void (*fn)(const float*, const void*, float*, float*, unsigned int*, int, int, int, float, size_t, size_t, size_t, PeerStore, int, int);
-            int warps, lpr;
-            if (quant)
-                gemv_pick<GemvS8>(k->gemv_variant, &fn, &warps, &lpr, (int)k->M, k->prm.group_k != 0);
-            else
-                gemv_pick<GemvF32>(k->gemv_variant, &fn, &warps, &lpr, (int)k->M);
+            const GemvFn fn = (quant ? gemv_pick<GemvS8>(k->gemv_variant, (int)k->M, k->prm.group_k != 0) : gemv_pick<GemvF32>(k->gemv_variant, (int)k->M)).fn;
             const size_t group_k = k->prm.group_k;
             const float scale = quant ? (group_k ? 1.0f : k->prm.absmax) / 127.0f : 1.0f;
             const size_t wstride = quant ? (size_t)K * N + (group_k ? ceil_div(K, group_k) * N * 4 : 0) : (size_t)K * N * 4;
