@@ -173,6 +173,14 @@ B200MM_API int b200mm_mm_host(b200mm_ctx* ctx, b200mm_kernel* kern, const void* 
                               size_t bytesB, void* hostC, size_t bytesC, b200mm_buffer* dA, b200mm_buffer* dB,
                               b200mm_buffer* dC);
 
+/* ---- device-free introspection of the SGEMM_TC3X work schedule (no GPU needed; used by the CPU tests) --------------
+ * out = {grid, full_waves, chains_per_tile, k_split, tiles, stream_k_units} for a bn x 128 tile, bk-deep stages, `sms` SMs. */
+B200MM_API int b200mm_tc3x_schedule(size_t M, size_t N, size_t K, int bn, int bk, int sms, int pure_stream_k, int out[6]);
+/* Runs the kernel's own segment iterator for every CTA on the host and counts how often each (tile, chain) unit is
+ * visited: cover[tile * chains_per_tile + chain] += 1 (caller zero-fills; cover_len >= tiles * chains_per_tile). */
+B200MM_API int b200mm_tc3x_schedule_cover(size_t M, size_t N, size_t K, int bn, int bk, int sms, int pure_stream_k, uint16_t* cover,
+                                          size_t cover_len, int* max_segments_per_cta, int* max_chains_per_cta);
+
 /* ---- timing: CUDA events on the ctx stream (the reference uses Instant::now, src/harness.rs:225) */
 B200MM_API int b200mm_timer_begin(b200mm_ctx* ctx);
 B200MM_API int b200mm_timer_end(b200mm_ctx* ctx, float* elapsed_ms); /* records, synchronises, returns ms */

@@ -184,3 +184,50 @@ def test_grouped_codec_zero_group_and_asserts():
         sint8_quantize_grouped(W, 128, 8, 0)
     with pytest.raises(B200mmError):
         sint8_dequantize_grouped(packed[:-1], 128, 8, 128)
+
+
+TC3X_SHAPES = [(4096, 4096, 4096), (16384, 2048, 16384), (128, 4096, 4096), (256, 4096, 4096), (512, 4096, 4096), (1024, 4096, 4096),
+               (2048, 4096, 4096), (1000, 520, 300), (128, 256, 256), (128, 128, 16), (4096, 4096, 100), (300, 36, 4100), (19000, 256, 512)]
+
+
+@pytest.mark.parametrize("shape", TC3X_SHAPES)
+@pytest.mark.parametrize("cfg", [(256, 16), (256, 32), (128, 32)])
+@pytest.mark.parametrize("pure", [0, 1])
+def test_tc3x_schedule_covers_every_unit_once(shape, cfg, pure):
+    """The SGEMM_TC3X work schedule (hybrid waves + stream-K, or the uniform k-split when tiles < SMs) as the kernel's own
+    segment iterator walks it, run on the host for all CTAs: every (tile, chain) unit exactly once, grid <= SMs."""
+    from wgpu_mm_b200 import lib
+    M, N, K = shape
+    bn, bk = cfg
+    sms = 148
+    out = (C.c_int * 6)()
+    assert lib().b200mm_tc3x_schedule(M, N, K, bn, bk, sms, pure, out) == 0
+    grid, full_waves, cpt, k_split, tiles, sk_units = list(out)
+    assert tiles == -(-M // 128) * -(-N // bn) and cpt == -(-(-(-K // bk)) // (256 // bk))
+    assert 1 <= grid <= sms
+    cover = np.zeros(tiles * cpt, dtype=np.uint16)
+    mseg, mch = C.c_int(), C.c_int()
+    assert lib().b200mm_tc3x_schedule_cover(M, N, K, bn, bk, sms, pure, cover.ctypes.data_as(C.c_void_p), cover.size, C.byref(mseg), C.byref(mch)) == 0
+    assert (cover == 1).all(), f"units visited {np.bincount(cover)} times"
+    assert full_waves * grid * cpt + sk_units == tiles * cpt
+    # balance: whole-tile waves plus an equal share (rounded up) of the stream-K units
+    assert mch.value <= full_waves * cpt + -(-sk_units // grid)
+    if k_split and not pure:
+        # fewer tiles than SMs: one segment per CTA, every tile cut into the same k_split slices
+        assert tiles < sms and cpt % k_split == 0 and grid == tiles * k_split and tiles * k_split <= sms
+        assert mseg.value == 1 and mch.value == cpt // k_split
+        assert all(cpt % d or tiles * d > sms for d in range(k_split + 1, cpt + 1))  # k_split is the largest admissible divisor
+
+
+def test_tc3x_schedule_reference_points():
+    """The cases quoted in DESIGN.md 4.1."""
+    from wgpu_mm_b200 import lib
+    out = (C.c_int * 6)()
+    lib().b200mm_tc3x_schedule(4096, 4096, 4096, 256, 16, 148, 0, out)
+    assert list(out) == [148, 3, 16, 0, 512, 68 * 16]  # 3 whole waves + 68 tiles split 148 ways
+    lib().b200mm_tc3x_schedule(256, 4096, 4096, 256, 16, 148, 0, out)
+    assert list(out)[:5] == [128, 0, 16, 4, 32]  # the 256-row panels of the host-buffer path: 32 tiles x 4 k-slices
+    lib().b200mm_tc3x_schedule(1024, 4096, 4096, 256, 16, 148, 0, out)
+    assert list(out)[:5] == [128, 1, 16, 1, 128]  # one tile per CTA, in lock-step
+    assert lib().b200mm_tc3x_schedule(0, 4096, 4096, 256, 16, 148, 0, out) != 0
+    assert lib().b200mm_tc3x_schedule(128, 128, 128, 192, 16, 148, 0, out) != 0

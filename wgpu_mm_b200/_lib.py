@@ -148,6 +148,8 @@ def _declare(l: C.CDLL) -> None:
     l.b200mm_kernel_set_peers.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), sz, sz]
     l.b200mm_peer_barrier.argtypes = [vp, vp, C.POINTER(vp), C.c_int, C.c_int]
     l.b200mm_unshard_columns.argtypes = [vp, vp, vp, sz, sz, C.c_int]
+    l.b200mm_tc3x_schedule.argtypes = [sz, sz, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    l.b200mm_tc3x_schedule_cover.argtypes = [sz, sz, sz, C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     # wgpu_mm_c.h
     l.wgpumm_run_test.argtypes = [C.c_char_p, sz, sz, sz, C.c_uint64, C.c_int, C.c_int, C.POINTER(ReportC)]
     l.wgpumm_last_panic.restype = C.c_char_p

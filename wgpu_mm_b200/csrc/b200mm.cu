@@ -586,28 +586,14 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     const size_t a_bytes = M * K * sizeof(float), b_bytes = K * N * sizeof(float) + 128;
     const size_t a_al = ceil_div(a_bytes, 1024) * 1024, b_al = ceil_div(b_bytes, 1024) * 1024;
     k->tc_b_copy = (N % 32) != 0;
-    // stream-K schedule (see Tc3xArgs): units = tiles x chains, one contiguous range per CTA
-    const int bk = k->tc_bk, chain = 256 / bk;
-    const size_t num_kb = ceil_div(K, bk);
-    k->tc_cpt = (int)ceil_div(num_kb, chain);
-    const size_t tiles_all = ceil_div(M, 128) * ceil_div(N, k->tc_bn);
+    // schedule (see Tc3xArgs / tc3x_make_schedule): units = tiles x chains, one contiguous range per CTA
+    const int bk = k->tc_bk;
     const int sms = ctx->prop.multiProcessorCount;
-    // hybrid schedule: whole-tile waves while there are >= one tile per SM, stream-K over the remainder
-    int grid_x = (int)std::min<long long>((long long)tiles_all * k->tc_cpt, sms);
-    if ((long long)tiles_all < sms && k->prm.tune[1] != 1) {
-        // Fewer tiles than SMs (skinny M, and the row panels of the pipelined host-buffer path): plain stream-K gives every CTA a
-        // k-range that starts somewhere else, so CTAs that share an A row panel or a B column panel are never at the same k and
-        // nothing is reused out of L2 -- ncu at 1024 x 4096 x 4096: 966 MB of DRAM reads for 176 MB of operands, DRAM-bound.
-        // Instead split every tile into the same S k-slices (S | chains per tile, tiles x S <= SMs): one segment per CTA, all
-        // CTAs walk k in lock-step, and CTA b and b + S read the same k-slice of neighbouring tiles at the same time.
-        int S = 1;
-        for (int d = 1; d <= k->tc_cpt; ++d)
-            if (k->tc_cpt % d == 0 && (long long)tiles_all * d <= sms) S = d;
-        grid_x = (int)tiles_all * S;
-    }
-    k->tc_full_waves = (int)(tiles_all / grid_x);
-    if (k->prm.tune[1] == 1) k->tc_full_waves = 0;  // tune[1] = 1: pure stream-K (for experiments)
-    k->tc_sk_units = (long long)(tiles_all - (size_t)k->tc_full_waves * grid_x) * k->tc_cpt;
+    const Tc3xSchedule sched = tc3x_make_schedule(M, N, K, k->tc_bn, bk, sms, k->prm.tune[1] == 1);  // tune[1] = 1: pure stream-K (experiments)
+    const int grid_x = sched.grid;
+    k->tc_cpt = sched.chains_per_tile;
+    k->tc_full_waves = sched.full_waves;
+    k->tc_sk_units = sched.sk_units;
     const size_t part_bytes = (size_t)grid_x * 128 * k->tc_bn * sizeof(float);
     const size_t flag_bytes = ceil_div((size_t)grid_x * sizeof(unsigned int), 1024) * 1024;
     k->ws_bytes = (one_pass ? 0 : (a_al + b_al)) + (k->tc_b_copy ? b_al : 0) + part_bytes + flag_bytes;
@@ -1327,6 +1313,42 @@ extern "C" int b200mm_unshard_columns(b200mm_ctx* ctx, const void* gathered, voi
 // ------------------------------------------------------------------------------------------------
 // debug: tcgen05 bring-up probe (tools/probe_tc.py); not part of the public header
 // ------------------------------------------------------------------------------------------------
+// ---- device-free introspection of the tc3x schedule (tests/test_host.py) ---------------------------------------------------
+extern "C" int b200mm_tc3x_schedule(size_t M, size_t N, size_t K, int bn, int bk, int sms, int pure_stream_k, int out[6]) {
+    if (!out || !M || !N || !K || (bn != 128 && bn != 256) || (bk != 16 && bk != 32) || sms <= 0) return B200MM_ERR_INVALID;
+    const Tc3xSchedule sc = tc3x_make_schedule(M, N, K, bn, bk, sms, pure_stream_k != 0);
+    out[0] = sc.grid;
+    out[1] = sc.full_waves;
+    out[2] = sc.chains_per_tile;
+    out[3] = sc.k_split;
+    out[4] = (int)sc.tiles;
+    out[5] = (int)sc.sk_units;
+    return B200MM_OK;
+}
+
+extern "C" int b200mm_tc3x_schedule_cover(size_t M, size_t N, size_t K, int bn, int bk, int sms, int pure_stream_k, uint16_t* cover,
+                                          size_t cover_len, int* max_segments_per_cta, int* max_chains_per_cta) {
+    if (!cover || !M || !N || !K || (bn != 128 && bn != 256) || (bk != 16 && bk != 32) || sms <= 0) return B200MM_ERR_INVALID;
+    const Tc3xSchedule sc = tc3x_make_schedule(M, N, K, bn, bk, sms, pure_stream_k != 0);
+    if (cover_len < (size_t)sc.tiles * sc.chains_per_tile) return B200MM_ERR_INVALID;
+    int max_seg = 0, max_ch = 0;
+    for (int b = 0; b < sc.grid; ++b) {
+        SegIter it(sc.chains_per_tile, sc.full_waves, sc.sk_units, b, sc.grid);  // the very iterator the device roles run
+        int tile, c0, c1, skt, seg = 0, ch = 0;
+        while (it.next(tile, c0, c1, skt)) {
+            if (tile < 0 || tile >= sc.tiles || c0 < 0 || c1 > sc.chains_per_tile || c0 >= c1) return B200MM_ERR_INVALID;
+            for (int c = c0; c < c1; ++c) cover[(size_t)tile * sc.chains_per_tile + c]++;
+            ++seg;
+            ch += c1 - c0;
+        }
+        max_seg = std::max(max_seg, seg);
+        max_ch = std::max(max_ch, ch);
+    }
+    if (max_segments_per_cta) *max_segments_per_cta = max_seg;
+    if (max_chains_per_cta) *max_chains_per_cta = max_ch;
+    return B200MM_OK;
+}
+
 extern "C" B200MM_API int b200mm_debug_tc_probe(b200mm_ctx* ctx, const void* A, const void* B, size_t M, size_t N, size_t K,
                                                 const uint32_t* u32args /*11*/, void* dumpA, void* dumpB, void* dumpD) {
     if (!ctx || !A || !B) return fail(ctx, B200MM_ERR_INVALID, "probe: NULL argument");

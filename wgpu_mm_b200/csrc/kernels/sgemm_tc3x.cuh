@@ -213,18 +213,22 @@ struct Tc3xArgs {
     PeerStore peers;
 };
 
-struct SegIter {  // identical iteration in the producer, issuer and epilogue roles
+struct SegIter {  // identical iteration in the producer, issuer and epilogue roles (and on the host: b200mm_tc3x_schedule_cover)
     long long u, u1;
-    int cpt, wave, full_waves, sk_tile0;
-    __device__ SegIter(const Tc3xArgs& p) : cpt(p.chains_per_tile), wave(0), full_waves(p.full_waves) {
-        sk_tile0 = p.full_waves * (int)gridDim.x;
-        u = (long long)blockIdx.x * p.sk_units / gridDim.x;
-        u1 = (long long)(blockIdx.x + 1) * p.sk_units / gridDim.x;
+    int cpt, wave, full_waves, sk_tile0, block, grid;
+    __host__ __device__ SegIter(int chains_per_tile, int full_waves_, long long sk_units, int block_, int grid_)
+        : cpt(chains_per_tile), wave(0), full_waves(full_waves_), block(block_), grid(grid_) {
+        sk_tile0 = full_waves * grid;
+        u = (long long)block * sk_units / grid;
+        u1 = (long long)(block + 1) * sk_units / grid;
     }
+#ifdef __CUDACC__
+    __device__ SegIter(const Tc3xArgs& p) : SegIter(p.chains_per_tile, p.full_waves, p.sk_units, (int)blockIdx.x, (int)gridDim.x) {}
+#endif
     // c0 != 0 => contributor segment; c0 == 0 && c1 != cpt => owner of a split tile; sk_tile = tile index inside phase 2
-    __device__ bool next(int& tile, int& c0, int& c1, int& sk_tile) {
+    __host__ __device__ bool next(int& tile, int& c0, int& c1, int& sk_tile) {
         if (wave < full_waves) {
-            tile = wave * (int)gridDim.x + (int)blockIdx.x;
+            tile = wave * grid + block;
             c0 = 0;
             c1 = cpt;
             sk_tile = -1;
@@ -235,12 +239,43 @@ struct SegIter {  // identical iteration in the producer, issuer and epilogue ro
         sk_tile = (int)(u / cpt);
         tile = sk_tile0 + sk_tile;
         c0 = (int)(u % cpt);
-        const long long n = min((long long)(cpt - c0), u1 - u);
+        const long long left = u1 - u;
+        const long long n = (long long)(cpt - c0) < left ? (long long)(cpt - c0) : left;
         c1 = c0 + (int)n;
         u += n;
         return true;
     }
 };
+
+// Host-side choice of the schedule (used by setup_tc3x and by the device-free introspection entry points).
+struct Tc3xSchedule {
+    int chains_per_tile, full_waves, grid, k_split;  // k_split > 0: uniform split of every tile (tiles < SMs)
+    long long tiles, sk_units;
+};
+inline Tc3xSchedule tc3x_make_schedule(size_t M, size_t N, size_t K, int bn, int bk, int sms, bool pure_stream_k) {
+    Tc3xSchedule sc{};
+    const size_t chain = 256 / bk, num_kb = (K + bk - 1) / bk;
+    sc.chains_per_tile = (int)((num_kb + chain - 1) / chain);
+    sc.tiles = (long long)((M + 127) / 128) * (long long)((N + bn - 1) / bn);
+    // hybrid schedule: whole-tile waves while there is >= one tile per SM, stream-K over the remainder
+    long long grid = sc.tiles * sc.chains_per_tile < sms ? sc.tiles * sc.chains_per_tile : sms;
+    if (sc.tiles < sms && !pure_stream_k) {
+        // Fewer tiles than SMs (skinny M, and the row panels of the pipelined host-buffer path): plain stream-K gives every CTA a
+        // k-range that starts somewhere else, so CTAs that share an A row panel or a B column panel are never at the same k and
+        // nothing is reused out of L2 -- ncu at 1024 x 4096 x 4096: 966 MB of DRAM reads for 176 MB of operands, DRAM-bound.
+        // Instead split every tile into the same S k-slices (S | chains per tile, tiles x S <= SMs): one segment per CTA, all
+        // CTAs walk k in lock-step, and CTA b and b + S read the same k-slice of neighbouring tiles at the same time.
+        int S = 1;
+        for (int d = 1; d <= sc.chains_per_tile; ++d)
+            if (sc.chains_per_tile % d == 0 && sc.tiles * d <= sms) S = d;
+        grid = sc.tiles * S;
+        sc.k_split = S;
+    }
+    sc.grid = (int)grid;
+    sc.full_waves = pure_stream_k ? 0 : (int)(sc.tiles / grid);
+    sc.sk_units = (sc.tiles - (long long)sc.full_waves * grid) * sc.chains_per_tile;
+    return sc;
+}
 
 // CHAIN: number of k-blocks accumulated inside TMEM before the partial sum is folded into fp32 registers.
 // Measured on B200 (tools/debug_tc3x.py): the tensor core adds into its fp32 accumulator with truncation, so a
