@@ -1193,6 +1193,18 @@ extern "C" int b200mm_mm_host(b200mm_ctx* ctx, b200mm_kernel* kern, const void* 
     }
     b200mm_kernel* pk = kern->panel;
     const size_t Mp = M / P;
+    // Experiment (off by default): B200MM_HOST_ZEROCOPY_C=1 lets the epilogue store C straight into the caller's pinned host buffer
+    // over PCIe instead of staging it in dC and copying panel by panel.  Needs hostC to be device-accessible (b200mm_host_alloc).
+    bool zero_copy_c = false;
+    if (const char* z = getenv("B200MM_HOST_ZEROCOPY_C")) {
+        if (atoi(z) == 1) {
+            cudaPointerAttributes pa{};
+            zero_copy_c = cudaPointerGetAttributes(&pa, hostC) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer != nullptr &&
+                          (((uintptr_t)pa.devicePointer) & 15) == 0;
+            cudaGetLastError();
+            if (zero_copy_c) hostC = pa.devicePointer;  // same address under UVA
+        }
+    }
     cudaEvent_t ev_start = ctx->pipe_ev[0], ev_b = ctx->pipe_ev[1];
     // the copy streams must not run ahead of work already queued on the compute stream (it may still use dA/dB/dC)
     CU_TRY(ctx, cudaEventRecord(ev_start, ctx->stream));
@@ -1209,9 +1221,11 @@ extern "C" int b200mm_mm_host(b200mm_ctx* ctx, b200mm_kernel* kern, const void* 
     for (int i = 0; i < P; ++i) {
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[2 + i], 0));
         pk->tc_skip_b_split = (i > 0);  // B_lo from panel 0 is still in the panel kernel's workspace
-        rc = b200mm_launch_ptr(ctx, pk, (const char*)dA->ptr + (size_t)i * Mp * K * 4, dB->ptr, (char*)dC->ptr + (size_t)i * Mp * N * 4, nullptr);
+        rc = b200mm_launch_ptr(ctx, pk, (const char*)dA->ptr + (size_t)i * Mp * K * 4, dB->ptr,
+                               (zero_copy_c ? (char*)hostC : (char*)dC->ptr) + (size_t)i * Mp * N * 4, nullptr);
         pk->tc_skip_b_split = false;
         if (rc) return rc;
+        if (zero_copy_c) continue;  // C is already on its way to host memory; the final stream synchronize makes it visible
         CU_TRY(ctx, cudaEventRecord(ctx->pipe_ev[2 + 16 + i], ctx->stream));
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->pipe_ev[2 + 16 + i], 0));
         CU_TRY(ctx, cudaMemcpyAsync((char*)hostC + (size_t)i * Mp * N * 4, (const char*)dC->ptr + (size_t)i * Mp * N * 4, Mp * N * 4,
