@@ -137,6 +137,8 @@ def test_cpp_runner_reports_like_cargo(built_lib):
     assert os.path.exists(exe)
     r = subprocess.run([exe, "test_qdq"], capture_output=True, text=True)
     assert r.returncode == 0 and "test test_qdq ... ok" in r.stdout
+    r = subprocess.run([exe, "test_qdq_grouped"], capture_output=True, text=True)  # hand-computed words / scales of the grouped codec
+    assert r.returncode == 0 and "test test_qdq_grouped ... ok" in r.stdout
 
 
 @pytest.mark.parametrize("kng", [(256, 64, 128), (300, 16, 128), (64, 8, 128), (512, 32, 512)])
