@@ -540,7 +540,9 @@ ORACLE_API void oracle_qgemv_f64(const float* A, const uint32_t* Bq, double* C, 
  * src/quant.rs:17).  Same codec as oracle_sint8_quantize, but the absmax is taken per column n and
  * per block of group_k consecutive rows k: scales[g*N + n] = max |matrix[k*N + n]|, k in group g.
  * The last group may be ragged.  An all-zero group gives 0/0 = NaN -> `as i32` = 0, like the
- * reference would for an all-zero matrix.  Nothing in the reference pins this format.
+ * reference would for an all-zero matrix.  Nothing in the reference pins this format ("parity unpinned"
+ * w.r.t. the reference); the restatement is pinned by a hand-computed known-answer test on the test_qdq
+ * matrix and by equality with the reference codec when one group spans a column (tests/test_oracle.py).
  * ------------------------------------------------------------------------------------------ */
 ORACLE_API void oracle_sint8_quantize_grouped(const float* matrix, size_t K, size_t N, size_t group_k, uint32_t* out,
                                               float* scales) {

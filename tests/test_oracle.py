@@ -20,6 +20,29 @@ def test_qdq_golden(oracle):
     assert np.all(np.abs(m - deq) < g["roundtrip_tolerance"])
 
 
+def test_qdq_grouped_hand_computed(oracle):
+    """Per-group scales are an extension (the reference has one global absmax, src/quant.rs:17), so nothing in the reference pins
+    them; the oracle is pinned by hand instead, on the test_qdq matrix with 2-row groups: scales = column maxima per row pair,
+    0.1/1.0*127 = 12.7 -> 13, 0.5/1.2*127 = 52.9 -> 53, and every entry of rows 1 and 3 is its own group's absmax -> +-127.
+    group_k = K must reproduce the per-column global codec, and with one scale for everything the golden words of test_qdq."""
+    g = json.load(open(os.path.join(GOLD, "test_qdq.json")))
+    m = np.array(g["matrix"], dtype=np.float32)
+    words, scales = oracle.sint8_quantize_grouped(m, 4, 4, 2)
+    assert scales.tolist() == [[1.0, 1.0, np.float32(1.2), np.float32(1.2)]] * 2
+    b = lambda q: q & 0xFF
+    row0 = b(13) | b(-13) << 8 | b(53) << 16 | b(-53) << 24
+    assert [int(w) for w in words] == [row0, 0x817F817F, row0, 0x817F817F]
+    deq = oracle.sint8_dequantize_grouped(words, scales, 4, 4, 2).reshape(-1)
+    assert np.all(np.abs(m - deq) < 0.006)
+    # a matrix whose columns all share the global absmax: grouped (one group) == the reference codec == golden words
+    m2 = m.reshape(4, 4).copy()
+    m2[3] = [1.2, -1.2, 1.2, -1.2]  # now every column contains the global absmax
+    words1, scales1 = oracle.sint8_quantize_grouped(m2, 4, 4, 4)
+    gw, absmax = oracle.sint8_quantize(m2, 4, 4)
+    assert (scales1 == absmax).all() and np.array_equal(words1, gw)
+    assert [int(w) for w in gw[:3]] == g["words"][:3]  # rows 0-2 are still the reference's golden words
+
+
 def test_weight_stream_golden(oracle):
     g = json.load(open(os.path.join(GOLD, "weight_stream.json")))
     for c in g["cases"]:
