@@ -286,66 +286,75 @@ def run_single(args):
     free_sets(sets)
 
     if not args.no_extras:
-        # ---------------- GEMV fp32 1x4096 * 4096x16384: 4 weight sets = 1 GiB rotated (> L2) ----------------
-        Kv, Nv = 4096, 16384
-        gsets = make_sets(ctx, 1, Nv, Kv, 4, 300)
-        AT = int(w.Flags.AUTOTUNE)  # geometry / K-split count measured once at kernel creation (no-op when --gemv-variant is given)
-        kg = ctx.kernel(w.KernelId.GEMV_F32, 1, Nv, Kv, w.KernelParams(tune=(args.gemv_variant, 0, 0, 0), flags=AT))
-        ms = time_back_to_back(ctx, kg, gsets, 200, 20)
-        tot = ms * 40
-        gbytes = 4.0 * Kv * Nv + 4 * Kv + 4 * Nv
-        extras["gemv_f32_4096x16384"] = {"gbps": gbytes / (ms * 1e-3) / 1e9, "kernel_us": ms * 1e3, "geometry": list(kg.geometry()), "timing": "200 back-to-back PDL launches, 4 weight sets (1 GiB) rotated",
-                                         "roofline": {"bound": "hbm", "achieved": gbytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                                      "frac": gbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "frac_of_nominal_8000_gbs": gbytes / (ms * 1e-3) / 1e9 / 8000.0, "traffic": traffic.get("gemv_stream_kernel<GemvF32>@4096x16384"),
-                                                      "algorithmic_bytes": gbytes, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['_source']})"}}
-        kg.free(); free_sets(gsets)
-        # ---------------- qGEMV sint8 1x4096 * 4096x14336: 8 weight sets = 470 MB rotated (> L2) ----------------
-        Kq, Nq = 4096, 14336
-        qsets = make_sets(ctx, 1, Nq, Kq, 8, 500, quant=True)
-        kq = ctx.kernel(w.KernelId.QGEMV_SINT8, 1, Nq, Kq, w.KernelParams(absmax=2.0, batch=1, tune=(args.gemv_variant, 0, 0, 0), flags=AT))
-        ms = time_back_to_back(ctx, kq, qsets, 400, 40)
-        tot = ms * 80
-        qbytes = 1.0 * Kq * Nq + 4 * Kq + 4 * Nq
-        extras["qgemv_sint8_4096x14336"] = {"gbps": qbytes / (ms * 1e-3) / 1e9, "kernel_us": ms * 1e3, "geometry": list(kq.geometry()), "timing": "400 back-to-back PDL launches, 8 weight sets (470 MB) rotated",
-                                            "roofline": {"bound": "hbm", "achieved": qbytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                                         "frac": qbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "frac_of_nominal_8000_gbs": qbytes / (ms * 1e-3) / 1e9 / 8000.0, "traffic": traffic.get("gemv_stream_kernel<GemvS8>@4096x14336"),
-                                                         "algorithmic_bytes": qbytes, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['_source']})"}}
-        kq.free(); free_sets(qsets)
-        # ---------------- same shape with per-group scales (group_k = 128): weights + 1.8 MB of scales ----------------
-        gk = 128
-        qsets = make_sets(ctx, 1, Nq, Kq, 8, 600, quant=True, group_k=gk)
-        kq = ctx.kernel(w.KernelId.QGEMV_SINT8, 1, Nq, Kq, w.KernelParams(batch=1, group_k=gk, flags=AT))
-        ms = time_back_to_back(ctx, kq, qsets, 400, 40)
-        gqbytes = qbytes + 4.0 * (Kq // gk) * Nq
-        extras["qgemv_sint8_g128_4096x14336"] = {"gbps": gqbytes / (ms * 1e-3) / 1e9, "kernel_us": ms * 1e3, "algorithmic_bytes": gqbytes, "geometry": list(kq.geometry()),
-                                                 "frac_of_hbm_peak": gqbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                                 "timing": "400 back-to-back PDL launches, 8 weight sets rotated"}
-        kq.free(); free_sets(qsets)
+        try:  # a failing extra must never cost the headline line
+            # ---------------- GEMV fp32 1x4096 * 4096x16384: 4 weight sets = 1 GiB rotated (> L2) ----------------
+            Kv, Nv = 4096, 16384
+            gsets = make_sets(ctx, 1, Nv, Kv, 4, 300)
+            AT = int(w.Flags.AUTOTUNE)  # geometry / K-split count measured once at kernel creation (no-op when --gemv-variant is given)
+            kg = ctx.kernel(w.KernelId.GEMV_F32, 1, Nv, Kv, w.KernelParams(tune=(args.gemv_variant, 0, 0, 0), flags=AT))
+            ms = time_back_to_back(ctx, kg, gsets, 200, 20)
+            tot = ms * 40
+            gbytes = 4.0 * Kv * Nv + 4 * Kv + 4 * Nv
+            extras["gemv_f32_4096x16384"] = {"gbps": gbytes / (ms * 1e-3) / 1e9, "kernel_us": ms * 1e3, "geometry": list(kg.geometry()), "timing": "200 back-to-back PDL launches, 4 weight sets (1 GiB) rotated",
+                                             "roofline": {"bound": "hbm", "achieved": gbytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                                          "frac": gbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "frac_of_nominal_8000_gbs": gbytes / (ms * 1e-3) / 1e9 / 8000.0, "traffic": traffic.get("gemv_stream_kernel<GemvF32>@4096x16384"),
+                                                          "algorithmic_bytes": gbytes, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['_source']})"}}
+            kg.free(); free_sets(gsets)
+            # ---------------- qGEMV sint8 1x4096 * 4096x14336: 8 weight sets = 470 MB rotated (> L2) ----------------
+            Kq, Nq = 4096, 14336
+            qsets = make_sets(ctx, 1, Nq, Kq, 8, 500, quant=True)
+            kq = ctx.kernel(w.KernelId.QGEMV_SINT8, 1, Nq, Kq, w.KernelParams(absmax=2.0, batch=1, tune=(args.gemv_variant, 0, 0, 0), flags=AT))
+            ms = time_back_to_back(ctx, kq, qsets, 400, 40)
+            tot = ms * 80
+            qbytes = 1.0 * Kq * Nq + 4 * Kq + 4 * Nq
+            extras["qgemv_sint8_4096x14336"] = {"gbps": qbytes / (ms * 1e-3) / 1e9, "kernel_us": ms * 1e3, "geometry": list(kq.geometry()), "timing": "400 back-to-back PDL launches, 8 weight sets (470 MB) rotated",
+                                                "roofline": {"bound": "hbm", "achieved": qbytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                                             "frac": qbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "frac_of_nominal_8000_gbs": qbytes / (ms * 1e-3) / 1e9 / 8000.0, "traffic": traffic.get("gemv_stream_kernel<GemvS8>@4096x14336"),
+                                                             "algorithmic_bytes": qbytes, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['_source']})"}}
+            kq.free(); free_sets(qsets)
+            # ---------------- same shape with per-group scales (group_k = 128): weights + 1.8 MB of scales ----------------
+            gk = 128
+            qsets = make_sets(ctx, 1, Nq, Kq, 8, 600, quant=True, group_k=gk)
+            kq = ctx.kernel(w.KernelId.QGEMV_SINT8, 1, Nq, Kq, w.KernelParams(batch=1, group_k=gk, flags=AT))
+            ms = time_back_to_back(ctx, kq, qsets, 400, 40)
+            gqbytes = qbytes + 4.0 * (Kq // gk) * Nq
+            extras["qgemv_sint8_g128_4096x14336"] = {"gbps": gqbytes / (ms * 1e-3) / 1e9, "kernel_us": ms * 1e3, "algorithmic_bytes": gqbytes, "geometry": list(kq.geometry()),
+                                                     "frac_of_hbm_peak": gqbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                                     "timing": "400 back-to-back PDL launches, 8 weight sets rotated"}
+            kq.free(); free_sets(qsets)
+        except Exception as exc:  # noqa: BLE001
+            extras.setdefault("errors", {})["gemv"] = repr(exc)
 
     if not args.no_extras:
-        # ---------------- SGEMM 16384^3 on ONE GPU: the strong-scaling baseline of the N-sharded runs ----------------
-        Mb = 16384
-        kb = ctx.kernel(w.KernelId.SGEMM_TC3X, Mb, Mb, Mb, w.KernelParams(tune=tune))
-        bsets = make_sets(ctx, Mb, Mb, Mb, 1, 700)
-        tot, per = time_kernel_steps(ctx, kb, bsets, 3, 2)
-        bflop = 2.0 * Mb * Mb * Mb
-        extras["sgemm_tc3x_16384_1gpu"] = {"tflops": bflop / (tot / 3 * 1e-3) / 1e12, "ms_per_step": tot / 3, "kernel_ms": float(np.mean(per)),
-                                           "note": "same kernel and schedule as the N-sharded runs; sustained clocks (power cap) apply"}
-        kb.free(); free_sets(bsets)
+        try:  # a failing extra must never cost the headline line
+            # ---------------- SGEMM 16384^3 on ONE GPU: the strong-scaling baseline of the N-sharded runs ----------------
+            Mb = 16384
+            kb = ctx.kernel(w.KernelId.SGEMM_TC3X, Mb, Mb, Mb, w.KernelParams(tune=tune))
+            bsets = make_sets(ctx, Mb, Mb, Mb, 1, 700)
+            tot, per = time_kernel_steps(ctx, kb, bsets, 3, 2)
+            bflop = 2.0 * Mb * Mb * Mb
+            extras["sgemm_tc3x_16384_1gpu"] = {"tflops": bflop / (tot / 3 * 1e-3) / 1e12, "ms_per_step": tot / 3, "kernel_ms": float(np.mean(per)),
+                                               "note": "same kernel and schedule as the N-sharded runs; sustained clocks (power cap) apply"}
+            kb.free(); free_sets(bsets)
+        except Exception as exc:  # noqa: BLE001
+            extras.setdefault("errors", {})["sgemm_16384_1gpu"] = repr(exc)
 
     if not args.no_extras:
-        # ---------------- BASELINE configs[0]: the reference's own test shape (1024^3) through the host harness ----------------
-        # verify (max-abs-err <= 1e-3 vs mm_ref) -> 8 warm-up -> 10 timed launches + read-back, exactly src/harness.rs:170-248;
-        # "gflops" is the reference-style number (wall clock incl. the D2H of C), "kernel_gflops" the CUDA-event one
-        from wgpu_mm_b200 import harness as hz
-        h = {}
-        for entry in ("gemm_wonnx", "gemm_5", "sgemm_simt", "sgemm_tc3x"):
-            r = hz.test_harness(None, entry, (1024, 1024, 1024), False)
-            h[entry] = {"reference_style_gflops": r.gflops, "kernel_gflops": r.kernel_gflops, "max_abs_err": r.max_abs_err,
-                        "max_rel_err_f64": r.max_rel_err_f64}
-        r = hz.test_harness(None, "qgemv_1", (1, 1024, 1024), True)
-        h["qgemv_1"] = {"kernel_gbps": r.kernel_gbps, "max_abs_err": r.max_abs_err}
-        extras["harness_1024_reference_shapes"] = h
+        try:  # a failing extra must never cost the headline line
+            # ---------------- BASELINE configs[0]: the reference's own test shape (1024^3) through the host harness ----------------
+            # verify (max-abs-err <= 1e-3 vs mm_ref) -> 8 warm-up -> 10 timed launches + read-back, exactly src/harness.rs:170-248;
+            # "gflops" is the reference-style number (wall clock incl. the D2H of C), "kernel_gflops" the CUDA-event one
+            from wgpu_mm_b200 import harness as hz
+            h = {}
+            for entry in ("gemm_wonnx", "gemm_5", "sgemm_simt", "sgemm_tc3x"):
+                r = hz.test_harness(None, entry, (1024, 1024, 1024), False)
+                h[entry] = {"reference_style_gflops": r.gflops, "kernel_gflops": r.kernel_gflops, "max_abs_err": r.max_abs_err,
+                            "max_rel_err_f64": r.max_rel_err_f64}
+            r = hz.test_harness(None, "qgemv_1", (1, 1024, 1024), True)
+            h["qgemv_1"] = {"kernel_gbps": r.kernel_gbps, "max_abs_err": r.max_abs_err}
+            extras["harness_1024_reference_shapes"] = h
+        except Exception as exc:  # noqa: BLE001
+            extras.setdefault("errors", {})["harness_1024"] = repr(exc)
 
     # ---------------- CPU baseline (reported, not the target) ----------------
     cpu = None
