@@ -181,6 +181,11 @@ B200MM_API int b200mm_tc3x_schedule(size_t M, size_t N, size_t K, int bn, int bk
 B200MM_API int b200mm_tc3x_schedule_cover(size_t M, size_t N, size_t K, int bn, int bk, int sms, int pure_stream_k, uint16_t* cover,
                                           size_t cover_len, int* max_segments_per_cta, int* max_chains_per_cta);
 
+/* Replays the stream-K fix-up protocol (who waits on whom) on the host: *violations == 0 means every finisher CTA waits only
+ * on lower-numbered CTAs that do publish a part of the same tile, and the parts cover the tile exactly. */
+B200MM_API int b200mm_tc3x_schedule_replay(size_t M, size_t N, size_t K, int bn, int bk, int sms, int pure_stream_k, int* violations,
+                                           int* max_wait_list);
+
 /* ---- timing: CUDA events on the ctx stream (the reference uses Instant::now, src/harness.rs:225) */
 B200MM_API int b200mm_timer_begin(b200mm_ctx* ctx);
 B200MM_API int b200mm_timer_end(b200mm_ctx* ctx, float* elapsed_ms); /* records, synchronises, returns ms */

@@ -96,6 +96,7 @@ std::pair<Workload, KernelSpec> gemm3(Context& context);       // shaders/gemm3.
 // B200-native SGEMM (Workload is advisory: the library derives its own launch configuration)
 std::pair<Workload, KernelSpec> sgemm_simt(Context& context);
 std::pair<Workload, KernelSpec> sgemm_tc3x(Context& context);
+std::pair<Workload, KernelSpec> sgemm_tc3x_1x(Context& context);  // single-pass TF32: fails the gate at large K (panic-path tests)
 }  // namespace gemm
 
 namespace gemv {

@@ -26,6 +26,12 @@ typedef struct wgpumm_report {
  * wgpumm_last_panic() holds the message. */
 WGPUMM_API int wgpumm_run_test(const char* name, size_t M, size_t N, size_t K, uint64_t seed, int device, int verbose,
                                wgpumm_report* out);
+/* Same, but with the caller's own Workload and quantize_b, i.e. the full signature of test_harness (src/harness.rs:170-175):
+ * grid / block = Workload::count / ::size (NULL = what the entry point produced; for the faithful ports they become
+ * gridDim / blockDim), quantize_b 0 / 1 (< 0 = the entry point's own).  A quantize_b that does not match the kernel's B
+ * operand fails like wgpu's bind-group validation would ("binding 1 type mismatch"). */
+WGPUMM_API int wgpumm_run_test_ex(const char* name, size_t M, size_t N, size_t K, uint64_t seed, int device, int verbose,
+                                  const uint32_t* grid, const uint32_t* block, int quantize_b, wgpumm_report* out);
 WGPUMM_API const char* wgpumm_last_panic(void);
 
 /* Workload produced by an entry point at the given dims, without touching a GPU. */

@@ -91,6 +91,44 @@ def test_mae_gate_panics(gpu_ctx):
     kern.free()
 
 
+def test_harness_panics_mae_too_high(gpu_ctx):
+    """The harness's own panic path (src/harness.rs:82-84): single-pass TF32 through test_harness at K = 4096 must raise
+    with the reference's message and the TOLERANCE status."""
+    import wgpu_mm_b200 as w
+    from wgpu_mm_b200 import gemm, harness
+    context = {}
+    dims = gemm.insert_matrix_dims(context, (128, 256, 4096))
+    workload, shader = gemm.sgemm_tc3x_1x(context)
+    with pytest.raises(w.B200mmError) as ei:
+        harness.test_harness(workload, shader, dims, False)
+    assert "MAE too high" in str(ei.value) and ei.value.code == w._lib.ERR_TOLERANCE
+
+
+def test_harness_honours_workload_and_quantize_b(gpu_ctx):
+    """test_harness(workload, shader, dims, quantize_b) passes both through (src/harness.rs:170-175, 197, 201-206): a
+    caller-made Workload is what gets dispatched, and a quantize_b that contradicts the kernel's B operand fails."""
+    import wgpu_mm_b200 as w
+    from wgpu_mm_b200 import gemm, gemv, harness
+    from wgpu_mm_b200.workload import Workload, WorkgroupCount, WorkgroupSize
+    context = {}
+    dims = gemm.insert_matrix_dims(context, (64, 64, 64))
+    _, shader = gemm.gemm_1(context)
+    mine = Workload(WorkgroupCount(8, 8, 1), WorkgroupSize(8, 8, 1))  # gemm_1 is guarded: any covering grid works
+    rep = harness.test_harness(mine, shader, dims, False)
+    assert rep.grid == (8, 8, 1) and rep.block == (8, 8, 1) and rep.max_abs_err <= 1e-3
+    short = Workload(WorkgroupCount(1, 1, 1), WorkgroupSize(8, 8, 1))  # covers an 8 x 8 corner only -> the gate must trip
+    with pytest.raises(w.B200mmError):
+        harness.test_harness(short, shader, dims, False)
+    with pytest.raises(w.B200mmError) as ei:
+        harness.test_harness(None, shader, dims, True)
+    assert "binding 1" in str(ei.value)
+    context = {}
+    dims = gemv.insert_matrix_dims(context)
+    _, shader = gemv.qgemv_1(context)
+    with pytest.raises(w.B200mmError):
+        harness.test_harness(None, shader, dims, False)
+
+
 def test_cpp_runner_like_cargo_test(gpu_ctx):
     exe = os.path.join(ROOT, "wgpu_mm_b200", "lib", "wgpu_mm_tests")
     r = subprocess.run([exe, "test_gemm_5"], capture_output=True, text=True, timeout=300)

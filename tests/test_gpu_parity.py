@@ -256,6 +256,24 @@ def test_qgemv_batched(gpu_ctx, oracle, kid_name):
         assert oracle.max_abs_err(got[b:b + 1], oracle.qgemv_ref(x[b:b + 1], Ws[b], 1, N, K, 2.0)) <= GATE
 
 
+def test_qgemv_1_port_batch_guard(gpu_ctx, oracle):
+    """workgroup_size_y = 2 with batch = 3 dispatches 4 rows of invocations; the 4th must not touch memory (guard canary)."""
+    import wgpu_mm_b200 as w
+    K, N, batch = 64, 64, 3
+    x = oracle.generate_weight_data(26, batch, K)
+    Bq = np.concatenate([oracle.sint8_quantize(oracle.generate_weight_data(40 + b, K, N), K, N)[0] for b in range(batch)])
+    kern = gpu_ctx.kernel(w.KernelId.QGEMV_1, 1, N, K, w.KernelParams(absmax=2.0, batch=batch, workgroup_size=(8, 2, 1)))
+    dx, dB = gpu_ctx.buffer_from(x), gpu_ctx.buffer_from(Bq)
+    dy = gpu_ctx.buffer_from(np.full((batch + 1) * N, 7.0, dtype=np.float32))  # one canary row behind the batch
+    gpu_ctx.launch(kern, dx, dB, dy)
+    got = dy.read(np.float32).reshape(batch + 1, N)
+    assert np.array_equal(got[:batch], oracle.wgsl_qgemv_1(x, Bq, N, K, 2.0, batch=batch))
+    assert (got[batch] == 7.0).all()
+    for b in (dx, dB, dy):
+        b.free()
+    kern.free()
+
+
 GROUPED = [(1024, 1024, 128), (4096, 14336, 128), (4096, 14336, 256), (1000, 1040, 128), (64, 64, 128), (2048, 512, 2048),
            (1536, 256, 512), (4096, 4096, 4096)]
 

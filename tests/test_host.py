@@ -221,6 +221,28 @@ def test_tc3x_schedule_covers_every_unit_once(shape, cfg, pure):
         assert all(cpt % d or tiles * d > sms for d in range(k_split + 1, cpt + 1))  # k_split is the largest admissible divisor
 
 
+# shapes where stream-K units < CTAs, so some CTAs have an empty range (the advisor's hang list) + the regular ones
+TC3X_REPLAY_SHAPES = TC3X_SHAPES + [(4096, 4096, 512), (16384, 16384, 512), (4096, 14336, 512), (4096, 4096, 256), (4224, 4096, 768),
+                                    (19072, 512, 1024), (16384, 16384, 16384)]
+
+
+@pytest.mark.parametrize("shape", TC3X_REPLAY_SHAPES)
+@pytest.mark.parametrize("cfg", [(256, 16), (256, 32), (128, 32)])
+@pytest.mark.parametrize("pure", [0, 1])
+def test_tc3x_stream_k_fixup_protocol_replay(shape, cfg, pure):
+    """Replays the owner/contributor dependency graph of the stream-K tail with the kernel's own contributor rule: a finisher
+    waits only on lower-numbered CTAs that really publish a part of its tile (never on a CTA with an empty range -- the round-1
+    hang at 4096 x 4096 x 512), and the published parts plus its own chains cover the tile exactly."""
+    from wgpu_mm_b200 import lib
+    M, N, K = shape
+    bn, bk = cfg
+    for sms in (148, 132, 7):
+        bad, mw = C.c_int(-1), C.c_int()
+        assert lib().b200mm_tc3x_schedule_replay(M, N, K, bn, bk, sms, pure, C.byref(bad), C.byref(mw)) == 0
+        assert bad.value == 0, f"{bad.value} protocol violations at {shape} {cfg} sms={sms}"
+        assert mw.value <= max(1, -(-(-(-K // bk)) // (256 // bk)))  # at most chains_per_tile - 1 parts per tile (+ slack for 1)
+
+
 def test_tc3x_schedule_reference_points():
     """The cases quoted in DESIGN.md 4.1."""
     from wgpu_mm_b200 import lib

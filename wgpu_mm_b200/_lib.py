@@ -150,8 +150,10 @@ def _declare(l: C.CDLL) -> None:
     l.b200mm_unshard_columns.argtypes = [vp, vp, vp, sz, sz, C.c_int]
     l.b200mm_tc3x_schedule.argtypes = [sz, sz, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     l.b200mm_tc3x_schedule_cover.argtypes = [sz, sz, sz, C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    l.b200mm_tc3x_schedule_replay.argtypes = [sz, sz, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     # wgpu_mm_c.h
     l.wgpumm_run_test.argtypes = [C.c_char_p, sz, sz, sz, C.c_uint64, C.c_int, C.c_int, C.POINTER(ReportC)]
+    l.wgpumm_run_test_ex.argtypes = [C.c_char_p, sz, sz, sz, C.c_uint64, C.c_int, C.c_int, u32p, u32p, C.c_int, C.POINTER(ReportC)]
     l.wgpumm_last_panic.restype = C.c_char_p
     l.wgpumm_entry_workload.argtypes = [C.c_char_p, sz, sz, sz, u32p, u32p, C.POINTER(C.c_int)]
     l.wgpumm_sint8_quantize.argtypes = [vp, sz, sz, vp, C.POINTER(C.c_float)]

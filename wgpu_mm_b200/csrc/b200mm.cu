@@ -1021,7 +1021,7 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
         case B200MM_K_BRAM8X8: wgsl::bram<<<grid, k->block, 0, s>>>((const float4*)A, (const float4*)B, (float4*)C, M, N, K); break;
         case B200MM_K_GEMM3: wgsl::gemm3<<<grid, k->block, 0, s>>>((const float4*)A, (const float4*)B, (float4*)C, M, N, K); break;
         case B200MM_K_QGEMV_1:
-            wgsl::qgemv_1<<<grid, k->block, 0, s>>>((const float4*)A, (const uint32_t*)B, (float4*)C, N, K, k->prm.absmax);
+            wgsl::qgemv_1<<<grid, k->block, 0, s>>>((const float4*)A, (const uint32_t*)B, (float4*)C, N, K, k->prm.absmax, k->prm.batch ? k->prm.batch : 1u);
             break;
         case B200MM_K_SGEMM_SIMT: {
             const bool aligned = (M % SimtCfg::BM == 0) && (N % SimtCfg::BN == 0) && (K % SimtCfg::BK == 0);
@@ -1360,6 +1360,53 @@ extern "C" int b200mm_tc3x_schedule_cover(size_t M, size_t N, size_t K, int bn, 
     }
     if (max_segments_per_cta) *max_segments_per_cta = max_seg;
     if (max_chains_per_cta) *max_chains_per_cta = max_ch;
+    return B200MM_OK;
+}
+
+// Replays the stream-K fix-up protocol on the host with the kernel's own iterator and contributor rule: every finisher
+// must wait only on LOWER-numbered CTAs that really park a part of the same tile, and the parts must cover the tile
+// exactly.  Returns B200MM_OK and *violations == 0 when the protocol is consistent (no wait on a CTA that never publishes).
+extern "C" int b200mm_tc3x_schedule_replay(size_t M, size_t N, size_t K, int bn, int bk, int sms, int pure_stream_k, int* violations,
+                                           int* max_wait_list) {
+    if (!violations || !M || !N || !K || (bn != 128 && bn != 256) || (bk != 16 && bk != 32) || sms <= 0) return B200MM_ERR_INVALID;
+    const Tc3xSchedule sc = tc3x_make_schedule(M, N, K, bn, bk, sms, pure_stream_k != 0);
+    struct Parked { int tile, c0, c1; };
+    std::vector<Parked> parked(sc.grid, Parked{-1, 0, 0});
+    std::vector<int> publishes(sc.grid, 0);
+    for (int b = 0; b < sc.grid; ++b) {
+        SegIter it(sc.chains_per_tile, sc.full_waves, sc.sk_units, b, sc.grid);
+        int tile, c0, c1, skt;
+        while (it.next(tile, c0, c1, skt))
+            if (c1 != sc.chains_per_tile) {
+                parked[b] = Parked{tile, c0, c1};
+                publishes[b]++;
+            }
+    }
+    int bad = 0, max_wait = 0;
+    for (int b = 0; b < sc.grid; ++b) {
+        if (publishes[b] > 1) ++bad;  // one workspace slot / flag per CTA
+        SegIter it(sc.chains_per_tile, sc.full_waves, sc.sk_units, b, sc.grid);
+        int tile, c0, c1, skt;
+        while (it.next(tile, c0, c1, skt)) {
+            if (c1 != sc.chains_per_tile || c0 == 0) continue;
+            // finisher: the exact loop of the epilogue warps
+            int next_chain = 0, waits = 0;
+            const int j0 = tc3x_first_contributor(skt, sc.chains_per_tile, sc.sk_units, b, sc.grid);
+            for (int j = j0; j < b; ++j) {
+                if (tc3x_cta_is_empty(j, sc.sk_units, sc.grid)) continue;
+                ++waits;
+                if (j >= b || publishes[j] != 1 || parked[j].tile != tile || parked[j].c0 != next_chain) {
+                    ++bad;
+                    continue;
+                }
+                next_chain = parked[j].c1;
+            }
+            if (next_chain != c0) ++bad;  // the parts and the finisher's own chains must tile [0, cpt)
+            max_wait = std::max(max_wait, waits);
+        }
+    }
+    *violations = bad;
+    if (max_wait_list) *max_wait_list = max_wait;
     return B200MM_OK;
 }
 

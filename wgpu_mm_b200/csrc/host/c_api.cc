@@ -26,6 +26,7 @@ static const Entry* find_entry(const char* name) {
         {"gemm_wonnx", gemm::gemm_wonnx, false, false}, {"bram", gemm::bram, false, false},
         {"bram8x8", gemm::bram8x8, false, false},       {"gemm3", gemm::gemm3, false, false},
         {"sgemm_simt", gemm::sgemm_simt, false, false}, {"sgemm_tc3x", gemm::sgemm_tc3x, false, false},
+        {"sgemm_tc3x_1x", gemm::sgemm_tc3x_1x, false, false},
         {"qgemv_1", gemv::qgemv_1, true, true},         {"qgemv_sint8", gemv::qgemv_sint8, true, true},
         {"gemv_f32", gemv::gemv_f32, true, false},
         {"qgemv_sint8_grouped", [](Context& c) { return gemv::qgemv_sint8_grouped(c, 128); }, true, true},
@@ -64,6 +65,13 @@ extern "C" int wgpumm_entry_workload(const char* name, size_t M, size_t N, size_
 // One `cargo test test_<name>`: src/gemm.rs:158-170 (gemm_test! macro) / src/gemv.rs:41-49.
 extern "C" int wgpumm_run_test(const char* name, size_t M, size_t N, size_t K, uint64_t seed, int device, int verbose,
                                wgpumm_report* out) {
+    return wgpumm_run_test_ex(name, M, N, K, seed, device, verbose, nullptr, nullptr, -1, out);
+}
+
+// test_harness(workload, shader, dims, quantize_b) with the caller's own Workload and quantize_b (src/harness.rs:170-175):
+// grid/block NULL = what the entry point produced; quantize_b < 0 = the entry point's own operand type.
+extern "C" int wgpumm_run_test_ex(const char* name, size_t M, size_t N, size_t K, uint64_t seed, int device, int verbose,
+                                  const uint32_t* grid, const uint32_t* block, int quantize_b, wgpumm_report* out) {
     const Entry* e = name ? find_entry(name) : nullptr;
     if (!e) {
         g_panic = std::string("unknown entry point ") + (name ? name : "(null)");
@@ -73,11 +81,17 @@ extern "C" int wgpumm_run_test(const char* name, size_t M, size_t N, size_t K, u
         Context ctx;
         const Dims dims = e->is_gemv ? gemv::insert_matrix_dims(ctx, Dims{M, N, K}) : gemm::insert_matrix_dims(ctx, Dims{M, N, K});
         auto ws = e->fn(ctx);
+        if (grid || block) {
+            const WorkgroupCount cnt = grid ? WorkgroupCount{grid[0], grid[1], grid[2]} : ws.first.count();
+            const WorkgroupSize sz = block ? WorkgroupSize{block[0], block[1], block[2]} : ws.first.size();
+            ws.first = Workload(cnt, sz);
+        }
+        const bool qb = quantize_b < 0 ? e->quantize_b : quantize_b != 0;
         HarnessOptions opt;
         if (seed) opt.seed = seed;
         opt.device = device;
         opt.verbose = verbose != 0;
-        HarnessReport r = test_harness(ws.first, ws.second, dims, e->quantize_b, opt);
+        HarnessReport r = test_harness(ws.first, ws.second, dims, qb, opt);
         if (out) {
             out->max_abs_err = r.max_abs_err;
             out->max_rel_err_f64 = r.max_rel_err_f64;

@@ -129,6 +129,15 @@ std::pair<Workload, KernelSpec> sgemm_tc3x(Context& c) {
     return finish(c, Workload(WorkgroupCount((uint32_t)(tiles < 148 ? tiles : 148), 1, 1), WorkgroupSize(256, 1, 1)), B200MM_K_SGEMM_TC3X);
 }
 
+// single-pass TF32 (B200MM_F_TC3X_1X): misses the reference gate at large K by design -- it exists so that the harness's
+// own "MAE too high" panic (src/harness.rs:82-84) can be exercised end to end
+std::pair<Workload, KernelSpec> sgemm_tc3x_1x(Context& c) {
+    auto r = sgemm_tc3x(c);
+    r.second.name = "sgemm_tc3x_1x";
+    r.second.params.flags |= B200MM_F_TC3X_1X;
+    return r;
+}
+
 }  // namespace gemm
 
 namespace gemv {

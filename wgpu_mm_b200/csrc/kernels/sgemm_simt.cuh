@@ -37,8 +37,9 @@ struct SimtCfg {
 // full C on each peer GPU (NVLink peer mappings), see b200mm_kernel_set_peers.
 // Schedule.  One CTA per tile (hardware block scheduler, 2 CTAs resident per SM).  When a problem has fewer tiles
 // than resident CTAs, each tile is cut into `split` K-parts (CTA = tile * split + part) so that all SMs have work.
-// Part 0 owns the tile: it adds the partial tiles the other parts parked in `partial` (flag = epoch) in part order
-// (deterministic) and stores C.  All CTAs of such a launch are co-resident, so the owner's wait cannot deadlock.
+// The LAST part owns the tile: it adds the partial tiles the lower parts parked in `partial` (flag = epoch) in part order
+// (deterministic) and stores C.  The owner only waits on lower-numbered CTAs, which the hardware dispatches first, so
+// the wait cannot deadlock even when the launch is not fully co-resident.
 // (Measured and rejected: a persistent loop -- extra live state pushed the main loop over the 128-register budget and
 // ptxas sank the prefetch; splitting only the partial last wave of a large problem -- no gain.)
 struct SimtSched {
@@ -198,7 +199,7 @@ sgemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, floa
             __syncthreads();
         }
 
-        if (part != 0) {
+        if (part != nparts - 1) {
             // K-part of a split tile: park the partial tile for the owner (thread-major float4 layout, coalesced)
             float4* slot = sched.partial + (size_t)blockIdx.x * (BM * BN / 4);
 #pragma unroll
@@ -211,13 +212,14 @@ sgemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, floa
             if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(sched.flags + blockIdx.x), "r"(sched.epoch) : "memory");
             return;
         }
-        for (int pp = 1; pp < nparts; ++pp) {
-            // owner: add the other parts in part order (deterministic)
+        for (int pp = 0; pp < nparts - 1; ++pp) {
+            // owner (last part): add the lower parts in part order (deterministic); they have lower block indices
+            const unsigned int src = blockIdx.x - (unsigned)(nparts - 1) + (unsigned)pp;
             unsigned int seen;
             do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sched.flags + blockIdx.x + pp) : "memory");
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sched.flags + src) : "memory");
             } while (seen != sched.epoch);
-            const float4* slot = sched.partial + (size_t)(blockIdx.x + pp) * (BM * BN / 4);
+            const float4* slot = sched.partial + (size_t)src * (BM * BN / 4);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll

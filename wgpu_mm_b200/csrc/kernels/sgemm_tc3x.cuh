@@ -200,10 +200,13 @@ struct Tc3xArgs {
     // so the CTAs of a wave walk K in lock-step and share operand panels in L2.  Phase 2 (stream-K) covers the
     // remaining tiles (num_tiles % gridDim.x, or all of them when there are fewer tiles than CTAs): their
     // (tile, chain) units, in tile-major order, are cut into gridDim.x equal contiguous ranges.  A CTA whose range
-    // starts inside a tile ("contributor") parks its partial accumulators in partial[blockIdx.x] and raises
-    // flags[blockIdx.x] = epoch; the CTA that holds chain 0 of the tile ("owner") adds the contributions of the
-    // following CTAs in CTA order (deterministic) and stores C.  4096^3: 512 tiles on 148 SMs = 3 waves + 68 tiles
-    // split 148 ways instead of a 4th wave that leaves 80 SMs idle.
+    // ENDS inside a tile ("contributor": its last segment has c1 != chains_per_tile) parks its partial accumulators in
+    // partial[blockIdx.x] and raises flags[blockIdx.x] = epoch; the CTA that holds the LAST chain of the tile
+    // ("finisher") adds the contributions of the preceding CTAs in CTA order (deterministic) and stores C.  A CTA
+    // therefore only ever waits on LOWER-numbered CTAs, which the hardware dispatches first: the wait cannot deadlock
+    // even when the grid is not fully co-resident (another kernel holding SMs), and CTAs with an empty unit range
+    // (sk_units < gridDim.x) are never waited on.  4096^3: 512 tiles on 148 SMs = 3 waves + 68 tiles split 148 ways
+    // instead of a 4th wave that leaves 80 SMs idle.
     int chains_per_tile;
     int full_waves;
     long long sk_units;     // stream-K units = remaining tiles x chains_per_tile
@@ -225,7 +228,7 @@ struct SegIter {  // identical iteration in the producer, issuer and epilogue ro
 #ifdef __CUDACC__
     __device__ SegIter(const Tc3xArgs& p) : SegIter(p.chains_per_tile, p.full_waves, p.sk_units, (int)blockIdx.x, (int)gridDim.x) {}
 #endif
-    // c0 != 0 => contributor segment; c0 == 0 && c1 != cpt => owner of a split tile; sk_tile = tile index inside phase 2
+    // c1 != cpt => contributor segment (parked); c1 == cpt && c0 != 0 => finisher of a split tile; sk_tile = tile index inside phase 2
     __host__ __device__ bool next(int& tile, int& c0, int& c1, int& sk_tile) {
         if (wave < full_waves) {
             tile = wave * grid + block;
@@ -246,6 +249,20 @@ struct SegIter {  // identical iteration in the producer, issuer and epilogue ro
         return true;
     }
 };
+
+// Stream-K fix-up protocol, shared by the kernel and the host-side replay (b200mm_tc3x_schedule_replay): the finisher
+// of phase-2 tile `sk_tile` (CTA `block`, whose segment starts at chain c0 != 0) adds the parked parts of CTAs
+// [first, block) -- those whose unit range reaches into the tile -- skipping CTAs whose range is empty.
+__host__ __device__ inline long long tc3x_unit_start(int cta, long long sk_units, int grid) { return (long long)cta * sk_units / grid; }
+__host__ __device__ inline int tc3x_first_contributor(int sk_tile, int cpt, long long sk_units, int block, int grid) {
+    const long long tile_start = (long long)sk_tile * cpt;
+    int j = block;
+    while (j > 0 && tc3x_unit_start(j, sk_units, grid) > tile_start) --j;
+    return j;
+}
+__host__ __device__ inline bool tc3x_cta_is_empty(int cta, long long sk_units, int grid) {
+    return tc3x_unit_start(cta, sk_units, grid) == tc3x_unit_start(cta + 1, sk_units, grid);
+}
 
 // Host-side choice of the schedule (used by setup_tc3x and by the device-free introspection entry points).
 struct Tc3xSchedule {
@@ -320,7 +337,7 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
-    // tiles-stored counter: epilogue warps -> replicator warp (fused multi-GPU all-gather)
+    // tiles-stored counters, one per epilogue warp: epilogue warps -> replicator warp (fused multi-GPU all-gather)
     auto tiles_done_ptr = [&]() { return reinterpret_cast<volatile unsigned int*>(smem_raw + (tmem_slot + 8 - smem_u32(smem_raw))); };
     auto sA_hi = [&](int s) { return smem_base + s * STAGE_BYTES; };
     auto sA_lo = [&](int s) { return smem_base + s * STAGE_BYTES + A_BYTES; };
@@ -348,7 +365,7 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             ptx::mbar_init(tempty_bar(s), Cfg::EPI_WARPS);  // one arrive per epilogue warp
         }
         ptx::fence_barrier_init();
-        *tiles_done_ptr() = 0;
+        for (int i = 0; i < Cfg::EPI_WARPS; ++i) tiles_done_ptr()[i] = 0;
     }
     if (warp == 2) {
         ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -462,9 +479,11 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             const float* src_base = p.peers.c[p.peers.rank];
             volatile unsigned int* tiles_done = tiles_done_ptr();
             while (it.next(t, c0, c1, skt)) {
-                if (c0 != 0) continue;  // contributor segments do not store C
+                if (c1 != p.chains_per_tile) continue;  // contributor segments do not store C
                 ++stored;
-                while (*tiles_done < stored * Cfg::EPI_WARPS) __nanosleep(200);
+                // every epilogue warp counts its own stored tiles: the tile is complete when ALL eight have reached `stored`
+                // (one aggregate counter would let seven fast warps that are already a tile ahead stand in for a slow one)
+                while (!__all_sync(0xffffffffu, tiles_done[lane & 7] >= stored)) __nanosleep(200);
                 __threadfence();
                 int tm, tn;
                 tile_coords(t, tm, tn);
@@ -532,8 +551,8 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
             }
-            if (c0 != 0) {
-                // contributor: this range starts inside the tile -> park the partial sums for the owner
+            if (c1 != p.chains_per_tile) {
+                // contributor: this range ends inside the tile -> park the partial sums for the finisher (a higher-numbered CTA)
                 float4* slot = p.partial + (size_t)blockIdx.x * (COLS / 4) * 256;
 #pragma unroll
                 for (int j = 0; j < COLS / 4; ++j) slot[j * 256 + etid] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
@@ -542,11 +561,12 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
                 if (etid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.flags + blockIdx.x), "r"(p.epoch) : "memory");
                 continue;
             }
-            if (c1 != p.chains_per_tile) {
-                // owner of a tile that continues in the following CTAs: add their parts in CTA order
-                const long long tile_end = (long long)(skt + 1) * p.chains_per_tile;
-                for (int j = blockIdx.x + 1; j < (int)gridDim.x; ++j) {
-                    if ((long long)j * p.sk_units / gridDim.x >= tile_end) break;
+            if (c0 != 0) {
+                // finisher of a tile that began in preceding CTAs: add their parts in CTA order.  Only lower-numbered,
+                // non-empty CTAs are waited on (see Tc3xArgs).
+                const int j0 = tc3x_first_contributor(skt, p.chains_per_tile, p.sk_units, (int)blockIdx.x, (int)gridDim.x);
+                for (int j = j0; j < (int)blockIdx.x; ++j) {
+                    if (tc3x_cta_is_empty(j, p.sk_units, (int)gridDim.x)) continue;
                     unsigned int seen;
                     do {
                         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.flags + j) : "memory");
@@ -592,7 +612,10 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             if (p.peers.world > 1) {
                 __threadfence();  // the tile is in (local) global memory before the replicator is told
                 __syncwarp();
-                if (lane == 0) atomicAdd(const_cast<unsigned int*>(tiles_done_ptr()), 1u);
+                if (lane == 0) {
+                    volatile unsigned int* td = tiles_done_ptr() + (warp - 4);
+                    *td = *td + 1u;  // single writer per counter
+                }
             }
         }
     }

@@ -275,11 +275,13 @@ __device__ __forceinline__ float4 unpack4x8snorm_scaled(uint32_t w, float absmax
 }
 
 // shaders/gemv/qgemv_1.wgsl:10-39; gid.y is the batch (offsets :12-14)
+// The shader has no bounds checks (wgpu's robust buffer access absorbs stray invocations); here invocations beyond the
+// N/4 outputs or the batch count return, so a workgroup_size_y that does not divide the batch cannot touch memory past the buffers.
 __global__ void qgemv_1(const float4* __restrict__ A, const uint32_t* __restrict__ B, float4* __restrict__ C, unsigned N,
-                        unsigned K, float absmax) {
+                        unsigned K, float absmax, unsigned batch) {
     const unsigned gx = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned gy = blockIdx.y * blockDim.y + threadIdx.y;
-    if (gx >= N / 4) return;
+    if (gx >= N / 4 || gy >= batch) return;
     const size_t left_offset = (size_t)gy * (K / 4), right_offset = (size_t)gy * ((size_t)K * N / 4),
                  output_offset = (size_t)gy * (N / 4);
     float res[4] = {0.f, 0.f, 0.f, 0.f};

@@ -21,4 +21,4 @@ def _entry(name):
 
 gemm_1, gemm_1v, gemm_2, gemm_3, gemm_4, gemm_5 = (_entry(n) for n in ("gemm_1", "gemm_1v", "gemm_2", "gemm_3", "gemm_4", "gemm_5"))
 gemm_wonnx, bram, bram8x8, gemm3 = (_entry(n) for n in ("gemm_wonnx", "bram", "bram8x8", "gemm3"))
-sgemm_simt, sgemm_tc3x = (_entry(n) for n in ("sgemm_simt", "sgemm_tc3x"))
+sgemm_simt, sgemm_tc3x, sgemm_tc3x_1x = (_entry(n) for n in ("sgemm_simt", "sgemm_tc3x", "sgemm_tc3x_1x"))
