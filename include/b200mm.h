@@ -133,6 +133,10 @@ B200MM_API size_t b200mm_buffer_bytes(const b200mm_buffer* buf);
 B200MM_API int b200mm_buffer_write(b200mm_ctx* ctx, b200mm_buffer* buf, size_t offset, const void* host, size_t bytes);
 /* Blocking device->host read of the whole range (to_cpu). */
 B200MM_API int b200mm_buffer_read(b200mm_ctx* ctx, const b200mm_buffer* buf, size_t offset, void* host, size_t bytes);
+/* Blocking read of a column panel: `rows` rows of width_bytes, row r taken from offset + r*src_pitch of the buffer and
+ * stored at host + r*dst_pitch (an N-sharded rank reads back only its own panel of the row-major C). */
+B200MM_API int b200mm_buffer_read_2d(b200mm_ctx* ctx, const b200mm_buffer* buf, size_t offset, size_t src_pitch, void* host,
+                                     size_t dst_pitch, size_t width_bytes, size_t rows);
 /* Pinned host memory helpers (the reference's staging buffers are wgpu-internal). */
 B200MM_API int b200mm_host_alloc(size_t bytes, void** out);
 B200MM_API int b200mm_host_free(void* p);
@@ -195,6 +199,9 @@ B200MM_API int b200mm_timer_end(b200mm_ctx* ctx, float* elapsed_ms); /* records,
  * read / enable, oldest first. */
 B200MM_API int b200mm_kernel_profile_enable(b200mm_ctx* ctx, b200mm_kernel* kern, int enable);
 B200MM_API int b200mm_kernel_profile_read(b200mm_ctx* ctx, b200mm_kernel* kern, float* ms_out, int max_n, int* n_out);
+/* Measurement tool: FP32 FMA-pipe ceiling of this device in TFLOP/s from a register-only microbenchmark (packed != 0: FFMA2,
+ * else scalar FFMA); the measured denominator of the SIMT SGEMM's roofline. */
+B200MM_API int b200mm_measure_fma_peak(b200mm_ctx* ctx, int packed, int iters, int reps, double* tflops_out);
 /* Overwrites a >L2-sized scratch buffer so the next launch starts with a cold L2. */
 B200MM_API int b200mm_flush_l2(b200mm_ctx* ctx);
 

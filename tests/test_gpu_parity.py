@@ -124,6 +124,58 @@ def test_sgemm_tc3x_ragged(gpu_ctx, oracle, shape):
     _check(oracle, got, A, B)
 
 
+@pytest.mark.parametrize("shape", [(4096, 4096, 512), (4096, 14336, 512), (19000, 256, 512), (4224, 4096, 768), (2048, 2048, 256)])
+def test_sgemm_tc3x_stream_k_tail_with_idle_ctas(gpu_ctx, oracle, shape):
+    """Shapes whose stream-K tail has fewer units than CTAs (some CTAs get an empty range) or exactly one chain per tile:
+    the round-1 fix-up spun forever on a CTA that never publishes (ADVICE r1, 4096 x 4096 x 512).  Sampled rows vs FP64
+    and mm_ref; two launches must agree bit for bit (fixed summation order)."""
+    import wgpu_mm_b200 as w
+    M, N, K = shape
+    A = oracle.generate_weight_data(13, M, K)
+    B = oracle.generate_weight_data(14, K, N)
+    rows = np.array(sorted({0, 1, 127, 128, M // 2 + 3, M - 129, M - 1}))
+    got = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K)
+    assert not np.isnan(got).any() and not (got == 123.25).any()
+    e, m = oracle.err_vs_f64(got[rows], oracle.mm_f64_rows(A, B, rows))
+    assert e / m <= REL_F64
+    assert oracle.max_abs_err(got[rows], oracle.mm_ref(A[rows], B)) <= GATE
+    # checksum of checksums over ALL tiles: column sums of C == (column sums of A) * B, in FP64
+    cs = A.astype(np.float64).sum(axis=0) @ B.astype(np.float64)
+    assert np.abs(got.astype(np.float64).sum(axis=0) - cs).max() <= 1e-6 * M * np.abs(cs).max() + 1e-3
+    again = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K)
+    assert np.array_equal(got, again)
+
+
+@pytest.mark.parametrize("kid_name", ["SGEMM_TC3X", "SGEMM_SIMT"])
+def test_split_k_fixup_survives_a_busy_device(gpu_ctx, oracle, kid_name):
+    """The split-K / stream-K finisher only waits on lower-numbered CTAs, so it cannot deadlock when the grid is not fully
+    co-resident: run 1024^3 (K-split over idle SMs in both kernels) while a second context keeps every SM busy."""
+    import wgpu_mm_b200 as w
+    kid = getattr(w.KernelId, kid_name)
+    M = N = K = 1024
+    A = oracle.generate_weight_data(15, M, K)
+    B = oracle.generate_weight_data(16, K, N)
+    quiet = _run(gpu_ctx, kid, A, B, M, N, K)
+    _check(oracle, quiet, A, B)
+    other = w.Context(0)
+    S = 2048
+    oa, ob, oc = other.buffer(S * S * 4), other.buffer(S * S * 4), other.buffer(S * S * 4)
+    oa.fill_weights(1, S * S); ob.fill_weights(2, S * S)
+    hog = other.kernel(w.KernelId.SGEMM_SIMT, S, S, S)
+    kern = gpu_ctx.kernel(kid, M, N, K)
+    dA, dB, dC = gpu_ctx.buffer_from(A), gpu_ctx.buffer_from(B), gpu_ctx.buffer_from(np.full(M * N, 123.25, dtype=np.float32))
+    for _ in range(40):
+        other.launch(hog, oa, ob, oc)  # ~0.3 ms each on its own stream: 512 CTAs, 2 per SM
+    for _ in range(10):
+        gpu_ctx.launch(kern, dA, dB, dC)
+    busy = dC.read(np.float32).reshape(M, N)
+    other.sync()
+    assert np.array_equal(busy, quiet)
+    for b in (oa, ob, oc, dA, dB, dC):
+        b.free()
+    hog.free(); kern.free(); other.close()
+
+
 def test_sgemm_tc3x_rejects_unaligned(gpu_ctx):
     import wgpu_mm_b200 as w
     with pytest.raises(w.B200mmError):

@@ -141,6 +141,8 @@ def _declare(l: C.CDLL) -> None:
     l.b200mm_timer_begin.argtypes = [vp]
     l.b200mm_timer_end.argtypes = [vp, C.POINTER(C.c_float)]
     l.b200mm_flush_l2.argtypes = [vp]
+    l.b200mm_buffer_read_2d.argtypes = [vp, vp, sz, sz, vp, sz, sz, sz]
+    l.b200mm_measure_fma_peak.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
     l.b200mm_kernel_profile_enable.argtypes = [vp, vp, C.c_int]
     l.b200mm_kernel_profile_read.argtypes = [vp, vp, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
     l.b200mm_ipc_export.argtypes = [vp, vp, vp]

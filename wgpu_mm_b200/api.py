@@ -130,6 +130,12 @@ class Context:
         check(lib().b200mm_timer_end(self._h, C.byref(ms)), self._h)
         return float(ms.value)
 
+    def measure_fma_peak(self, packed: bool = True, iters: int = 4096, reps: int = 3) -> float:
+        """Measurement tool: FP32 FMA-pipe ceiling (TFLOP/s) from a register-only FFMA2 / FFMA microbenchmark."""
+        out = C.c_double()
+        check(lib().b200mm_measure_fma_peak(self._h, 1 if packed else 0, iters, reps, C.byref(out)), self._h)
+        return float(out.value)
+
     def flush_l2(self):
         check(lib().b200mm_flush_l2(self._h), self._h)
 
@@ -167,6 +173,11 @@ class Buffer:
 
     def read_into(self, out: np.ndarray, offset: int = 0):
         check(lib().b200mm_buffer_read(self.ctx.handle, self._h, offset, out.ctypes.data_as(C.c_void_p), out.nbytes), self.ctx.handle)
+
+    def read_2d_into(self, out: np.ndarray, offset: int, src_pitch: int, width_bytes: int, rows: int):
+        """Blocking read of `rows` rows of width_bytes (row r from offset + r*src_pitch) into the contiguous array `out`."""
+        check(lib().b200mm_buffer_read_2d(self.ctx.handle, self._h, offset, src_pitch, out.ctypes.data_as(C.c_void_p), width_bytes,
+                                          width_bytes, rows), self.ctx.handle)
 
     def fill_weights(self, seed: int, n: int, offset: int = 0):
         check(lib().b200mm_buffer_fill_weights(self.ctx.handle, self._h, seed, offset, n), self.ctx.handle)

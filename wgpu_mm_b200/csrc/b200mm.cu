@@ -21,6 +21,7 @@
 #include "kernels/sgemm_tc3x.cuh"
 #include "kernels/wgsl_ports.cuh"
 #include "kernels/tc_probe.cuh"
+#include "kernels/peak_probe.cuh"
 
 using namespace b200mm;
 
@@ -279,6 +280,17 @@ extern "C" int b200mm_buffer_read(b200mm_ctx* ctx, const b200mm_buffer* buf, siz
     if (offset + bytes > buf->bytes) return fail(ctx, B200MM_ERR_INVALID, "Error reading buffer: range exceeds buffer");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     CU_TRY(ctx, cudaMemcpyAsync(host, (const char*)buf->ptr + offset, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200MM_OK;
+}
+
+extern "C" int b200mm_buffer_read_2d(b200mm_ctx* ctx, const b200mm_buffer* buf, size_t offset, size_t src_pitch, void* host, size_t dst_pitch,
+                                     size_t width_bytes, size_t rows) {
+    if (!ctx || !buf || !host) return fail(ctx, B200MM_ERR_INVALID, "buffer_read_2d: NULL argument");
+    if (width_bytes > src_pitch || width_bytes > dst_pitch) return fail(ctx, B200MM_ERR_INVALID, "buffer_read_2d: width exceeds a pitch");
+    if (rows && offset + (rows - 1) * src_pitch + width_bytes > buf->bytes) return fail(ctx, B200MM_ERR_INVALID, "Error reading buffer: range exceeds buffer");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaMemcpy2DAsync(host, dst_pitch, (const char*)buf->ptr + offset, src_pitch, width_bytes, rows, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return B200MM_OK;
 }
@@ -1407,6 +1419,33 @@ extern "C" int b200mm_tc3x_schedule_replay(size_t M, size_t N, size_t K, int bn,
     }
     *violations = bad;
     if (max_wait_list) *max_wait_list = max_wait;
+    return B200MM_OK;
+}
+
+// Measurement tool (bench.py "measured_peaks"): FP32 FMA-pipe throughput of the device in TFLOP/s, packed (FFMA2) or scalar
+// FFMA, best of `reps` timed launches of a register-only kernel (2 x 1024 threads per SM, 8 independent chains per thread).
+extern "C" int b200mm_measure_fma_peak(b200mm_ctx* ctx, int packed, int iters, int reps, double* tflops_out) {
+    if (!ctx || !tflops_out || iters <= 0 || reps <= 0) return fail(ctx, B200MM_ERR_INVALID, "measure_fma_peak: bad argument");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    float* sink = nullptr;
+    CU_TRY(ctx, cudaMalloc(&sink, 256));
+    const int blocks = ctx->prop.multiProcessorCount * 2;
+    float best = 1e30f;
+    for (int r = 0; r < reps + 1; ++r) {  // first launch warms up
+        CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        if (packed)
+            fma_peak_kernel<true><<<blocks, 1024, 0, ctx->stream>>>(sink, iters, 0.999f, 1e-3f);
+        else
+            fma_peak_kernel<false><<<blocks, 1024, 0, ctx->stream>>>(sink, iters, 0.999f, 1e-3f);
+        CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CU_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+        float ms = 0.f;
+        CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (r) best = std::min(best, ms);
+    }
+    cudaFree(sink);
+    const double flop = (double)blocks * 1024.0 * iters * 4.0 * 8.0 * 2.0 /*x and y*/ * 2.0 /*fma = 2 flop*/;
+    *tflops_out = flop / (best * 1e-3) / 1e12;
     return B200MM_OK;
 }
 
