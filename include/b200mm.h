@@ -94,6 +94,10 @@ typedef struct b200mm_kernel_params {
                                      * (geometry, K-split count) pairs once on scratch weights larger than L2 and keeps the fastest.  The
                                      * shape is baked into the kernel object as in the reference (src/gemm.rs:5-7), so this is the analogue
                                      * of picking the WGSL tile constants per shape; the result is deterministic per kernel OBJECT. */
+#define B200MM_F_CONST_B 0x10u      /* SGEMM_TC3X: B is a constant operand (weights): its tf32 lo part is computed on the first launch with a given
+                                     * B pointer and reused while the pointer stays the same (the per-launch split pass then covers A only).
+                                     * The caller promises not to change B's contents in place; pass a different buffer (or re-create the
+                                     * kernel object) when the weights change. */
 #define B200MM_F_PEER_STORE 0x2u    /* SGEMM_*: epilogue also stores the C panel to the peers set by b200mm_kernel_set_peers   */
 
 typedef struct b200mm_ctx b200mm_ctx;
@@ -216,6 +220,16 @@ B200MM_API int b200mm_ipc_import(b200mm_ctx* ctx, const void* handle64, size_t b
  * y vectors (ldc is ignored) and col_offset the first output of this rank's slice. */
 B200MM_API int b200mm_kernel_set_peers(b200mm_kernel* kern, int rank, int world, void* const* peer_c, size_t ldc,
                                        size_t col_offset);
+/* In-kernel cross-rank completion for the N-sharded GEMV kernels (after b200mm_kernel_set_peers, world >= 2): peer_flags[r] is
+ * rank r's mapping of a library-allocated, ZERO-INITIALISED flag array of >= world + 1 u32 (own entry = local).  Every launch
+ * then ends with the last CTA publishing a per-launch epoch to all ranks and waiting for theirs: when the kernel completes on
+ * the ctx stream, every rank's slice of this step has landed in the local y -- no barrier launch, no collective.  All ranks
+ * must launch the same number of times.  pingpong_stride (floats; 0 = off): successive launches alternate between two y
+ * buffers that distance apart (launch e writes y + (e & 1) * stride on every rank; e = b200mm_kernel_peer_epoch after the
+ * launch), so a fast rank's step e + 1 never overwrites the y a slower rank's consumer of step e is still reading.
+ * peer_flags == NULL switches back to caller-side synchronisation. */
+B200MM_API int b200mm_kernel_set_peer_flags(b200mm_kernel* kern, void* const* peer_flags, size_t pingpong_stride);
+B200MM_API unsigned int b200mm_kernel_peer_epoch(const b200mm_kernel* kern);
 /* Stream-ordered barrier across the ranks of one box without a collective library: `local_flags` is a
  * library-allocated, zero-initialised buffer of >= world u32 on every rank, `peer_flags[r]` its mapping on
  * rank r (b200mm_ipc_import; own entry = local).  The kernel stores a per-call epoch into slot `rank` of every

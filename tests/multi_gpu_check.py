@@ -68,7 +68,8 @@ def main():
                 want = oracle.mm_ref(x, Wf)
                 f64 = oracle.mm_f64(x, Wf)
             job = shard.ShardedGemv(ctx, Kv, Nv, plan, quant=quant, mode=mode, x_host=x, panel_host=panel)
-            job.step()
+            for _ in range(3):  # several steps: epochs advance, y ping-pongs (fused mode completes across ranks in-kernel)
+                job.step()
             got = job.result().reshape(1, Nv)
             e, m = oracle.err_vs_f64(got, f64)
             mae = oracle.max_abs_err(got, want)

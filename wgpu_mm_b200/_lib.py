@@ -41,6 +41,7 @@ class KernelId(enum.IntEnum):
 class Flags(enum.IntFlag):
     NONE = 0
     TC3X_1X = 0x1
+    CONST_B = 0x10
     PEER_STORE = 0x2
     SEQUENTIAL_K = 0x4
     AUTOTUNE = 0x8
@@ -148,6 +149,9 @@ def _declare(l: C.CDLL) -> None:
     l.b200mm_ipc_export.argtypes = [vp, vp, vp]
     l.b200mm_ipc_import.argtypes = [vp, vp, sz, C.POINTER(vp)]
     l.b200mm_kernel_set_peers.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), sz, sz]
+    l.b200mm_kernel_set_peer_flags.argtypes = [vp, C.POINTER(vp), sz]
+    l.b200mm_kernel_peer_epoch.argtypes = [vp]
+    l.b200mm_kernel_peer_epoch.restype = C.c_uint
     l.b200mm_peer_barrier.argtypes = [vp, vp, C.POINTER(vp), C.c_int, C.c_int]
     l.b200mm_unshard_columns.argtypes = [vp, vp, vp, sz, sz, C.c_int]
     l.b200mm_tc3x_schedule.argtypes = [sz, sz, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]

@@ -231,6 +231,15 @@ class Kernel:
         arr = (C.c_void_p * max(world, 1))(*[C.c_void_p(p) for p in peer_ptrs])
         check(lib().b200mm_kernel_set_peers(self._h, rank, world, arr, ldc, col_offset))
 
+    def set_peer_flags(self, peer_ptrs: Optional[Sequence[int]], pingpong_stride: int = 0):
+        """In-kernel cross-rank completion (GEMV): see b200mm_kernel_set_peer_flags."""
+        arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(p) for p in peer_ptrs]) if peer_ptrs else None
+        check(lib().b200mm_kernel_set_peer_flags(self._h, arr, pingpong_stride))
+
+    @property
+    def peer_epoch(self) -> int:
+        return int(lib().b200mm_kernel_peer_epoch(self._h))
+
     def free(self):
         if self._h is not None and self._h.value:
             lib().b200mm_kernel_free(self.ctx.handle, self._h)

@@ -69,6 +69,9 @@ struct b200mm_kernel {
     bool tc_b_copy = false;                               // ragged N: B is staged into a padded copy first
     float4* tc_partial = nullptr;
     unsigned int* tc_flags = nullptr;
+    unsigned int* tc_band_cnt = nullptr;  // in-kernel A split: per-band completion counters (see Tc3xArgs)
+    int tc_bands = 1, tc_prebands = 1;    // row bands of A; bands [0, prebands) are split by the pre-pass
+    const void* tc_const_b = nullptr;     // B200MM_F_CONST_B: the B whose lo part currently sits in the workspace
     unsigned int tc_epoch = 0;
     int tc_cpt = 1, tc_full_waves = 0;
     long long tc_sk_units = 0;
@@ -82,6 +85,8 @@ struct b200mm_kernel {
     int simt_tiles1 = 0, simt_tiles2 = 0;
     // multi-GPU
     PeerStore peers{};
+    unsigned int peer_epoch = 0;   // launches since set_peer_flags (in-kernel cross-rank completion)
+    size_t peer_pingpong = 0;      // GEMV: distance (floats) between the two y buffers alternated by epoch parity; 0 = one buffer
     // row-panel kernel object used by the pipelined host-buffer path (owned)
     b200mm_kernel* panel = nullptr;
     int panel_count = 0;
@@ -607,7 +612,17 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     k->tc_full_waves = sched.full_waves;
     k->tc_sk_units = sched.sk_units;
     const size_t part_bytes = (size_t)grid_x * 128 * k->tc_bn * sizeof(float);
-    const size_t flag_bytes = ceil_div((size_t)grid_x * sizeof(unsigned int), 1024) * 1024;
+    // In-kernel A split (Tc3xArgs): the pre-pass covers the row bands the first wave of tiles touches, warp 2 of every CTA
+    // does the rest while earlier bands are multiplied.  tune[3] = 1 keeps the whole split in the pre-pass (round-1 behaviour).
+    k->tc_bands = (int)ceil_div(M, (size_t)kTc3xBandRows);
+    {
+        const long long band_tiles = (long long)kTc3xGroupM * (long long)ceil_div(N, (size_t)k->tc_bn);
+        const long long first_wave = std::min<long long>(grid_x, sched.tiles);
+        long long pre = sched.full_waves == 0 ? k->tc_bands : (first_wave + band_tiles - 1) / band_tiles;
+        if (k->prm.tune[3] == 1 || one_pass) pre = k->tc_bands;
+        k->tc_prebands = (int)std::min<long long>(std::max<long long>(pre, 1), k->tc_bands);
+    }
+    const size_t flag_bytes = ceil_div(((size_t)grid_x + (size_t)k->tc_bands) * sizeof(unsigned int), 1024) * 1024;
     k->ws_bytes = (one_pass ? 0 : (a_al + b_al)) + (k->tc_b_copy ? b_al : 0) + part_bytes + flag_bytes;
     CU_TRY(ctx, cudaMalloc(&k->ws, k->ws_bytes));
     char* w = (char*)k->ws;
@@ -624,6 +639,7 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     k->tc_partial = (float4*)w;
     w += part_bytes;
     k->tc_flags = (unsigned int*)w;
+    k->tc_band_cnt = k->tc_flags + grid_x;
     CU_TRY(ctx, cudaMemsetAsync(k->ws, 0, k->ws_bytes, ctx->stream));
     int rc;
     if (!one_pass) {
@@ -971,12 +987,35 @@ extern "C" int b200mm_kernel_set_peers(b200mm_kernel* k, int rank, int world, vo
     return B200MM_OK;
 }
 
+extern "C" int b200mm_kernel_set_peer_flags(b200mm_kernel* k, void* const* peer_flags, size_t pingpong_stride) {
+    if (!k) return fail(nullptr, B200MM_ERR_INVALID, "set_peer_flags: kern is NULL");
+    if (k->id != B200MM_K_GEMV_F32 && k->id != B200MM_K_QGEMV_SINT8)
+        return fail(nullptr, B200MM_ERR_INVALID, "set_peer_flags: only the streaming GEMV kernels complete across ranks in-kernel");
+    if (k->peers.world < 2) return fail(nullptr, B200MM_ERR_INVALID, "set_peer_flags: call b200mm_kernel_set_peers first (world >= 2)");
+    for (int i = 0; i < 8; ++i) k->peers.flags[i] = nullptr;
+    k->peer_epoch = 0;
+    k->peer_pingpong = 0;
+    if (!peer_flags) return B200MM_OK;  // back to "caller synchronises the ranks" (b200mm_peer_barrier / a collective)
+    for (int i = 0; i < k->peers.world; ++i) {
+        if (!peer_flags[i]) return fail(nullptr, B200MM_ERR_INVALID, "set_peer_flags: peer %d is NULL", i);
+        k->peers.flags[i] = (unsigned int*)peer_flags[i];
+    }
+    k->peer_pingpong = pingpong_stride;
+    return B200MM_OK;
+}
+
+extern "C" unsigned int b200mm_kernel_peer_epoch(const b200mm_kernel* k) { return k ? k->peer_epoch : 0; }
+
 // ------------------------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------------------------
 template <class Cfg>
-static void launch_tc3x(b200mm_kernel* k, cudaStream_t s, float* C) {
+static cudaError_t launch_tc3x(b200mm_kernel* k, cudaStream_t s, const float* A, float* C) {
     Tc3xArgs a{};
+    a.A = A;
+    a.A_lo = k->a_lo;
+    a.band_cnt = k->tc_band_cnt;
+    a.prebands = k->tc_prebands;
     a.C = C;
     a.M = (int)k->M;
     a.N = (int)k->N;
@@ -992,7 +1031,19 @@ static void launch_tc3x(b200mm_kernel* k, cudaStream_t s, float* C) {
     a.epoch = ++k->tc_epoch;
     static_assert(Cfg::CHAIN * Cfg::BK == 256, "setup_tc3x assumes chains of 256 k");
     a.peers = k->peers;
-    sgemm_tc3x_kernel<Cfg><<<k->grid, k->block, k->smem, s>>>(k->tmAh, k->tmAl, k->tmBh, k->tmBl, a);
+    // Cooperative launch: the in-kernel A split makes every CTA's producer wait on the splitter warps of ALL CTAs, so the
+    // whole grid (<= one CTA per SM) must be co-resident; the driver refuses the launch otherwise instead of letting it hang.
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = k->grid;
+    cfg.blockDim = k->block;
+    cfg.dynamicSmemBytes = k->smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = (k->tc_prebands < k->tc_bands) ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, sgemm_tc3x_kernel<Cfg>, k->tmAh, k->tmAl, k->tmBh, k->tmBl, a);
 }
 
 extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* A, const void* B, void* C,
@@ -1074,23 +1125,32 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
                 if ((rc = make_tmap_mnmajor(ctx, &k->tmBh, (const float*)b_src, k->K, k->N, k->tc_bk, k->tc_bn))) return rc;
                 k->tc_b_src = b_src;
             }
+            cudaError_t le;
             if (one_pass) {
                 k->tmAl = k->tmAh;
                 k->tmBl = k->tmBh;
                 prof_begin();
-                launch_tc3x<Tc256x1>(k, s, Cf);
+                le = launch_tc3x<Tc256x1>(k, s, Af, Cf);
             } else {
-                split_lo_kernel<<<sms * 8, 256, 0, s>>>((const float4*)A, (float4*)k->a_lo, a4, (const float4*)B, (float4*)k->b_lo,
-                                                        k->tc_skip_b_split ? 0 : b4);
+                // pre-pass: B (unless its lo part is still valid) and the first row bands of A; the rest of A is split in-kernel
+                const size_t a4_pre = std::min<size_t>(a4, (size_t)k->tc_prebands * kTc3xBandRows * k->K / 4);
+                bool skip_b = k->tc_skip_b_split;
+                if (k->prm.flags & B200MM_F_CONST_B) {
+                    skip_b = skip_b || (k->tc_const_b == B);
+                    k->tc_const_b = B;
+                }
+                split_lo_kernel<<<sms * 8, 256, 0, s>>>((const float4*)A, (float4*)k->a_lo, a4_pre, (const float4*)B, (float4*)k->b_lo,
+                                                        skip_b ? 0 : b4);
                 ctx->launches += 1;
                 prof_begin();
                 if (k->tc_bn == 256 && k->tc_bk == 16)
-                    launch_tc3x<Tc256k16>(k, s, Cf);
+                    le = launch_tc3x<Tc256k16>(k, s, Af, Cf);
                 else if (k->tc_bn == 256)
-                    launch_tc3x<Tc256>(k, s, Cf);
+                    le = launch_tc3x<Tc256>(k, s, Af, Cf);
                 else
-                    launch_tc3x<Tc128>(k, s, Cf);
+                    le = launch_tc3x<Tc128>(k, s, Af, Cf);
             }
+            if (le != cudaSuccess) return fail(ctx, B200MM_ERR_CUDA, "sgemm_tc3x launch failed: %s", cudaGetErrorString(le));
             break;
         }
         case B200MM_K_GEMV_F32:
@@ -1121,8 +1181,14 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
                 attr[1].val.clusterDim.z = 1;
                 cfg.numAttrs = 2;
             }
+            PeerStore ps = k->peers;
+            if (ps.world > 1 && ps.flags[0]) {
+                ps.epoch = ++k->peer_epoch;
+                ps.signal_ctas = (unsigned)k->panels;  // one storing CTA per column panel (batch == 1 with peers)
+                ps.col0 += (size_t)(ps.epoch & 1u) * k->peer_pingpong;
+            }
             CU_TRY(ctx, cudaLaunchKernelEx(&cfg, fn, Af, (const void*)B, Cf, k->partial, k->tickets, (int)K, (int)N, k->rows_per_split, scale,
-                                           (size_t)k->M * K, wstride, (size_t)k->M * N, k->peers, cluster ? 1 : 0, (int)group_k));
+                                           (size_t)k->M * K, wstride, (size_t)k->M * N, ps, cluster ? 1 : 0, (int)group_k));
             break;
         }
         default:
@@ -1399,6 +1465,20 @@ extern "C" int b200mm_tc3x_schedule_replay(size_t M, size_t N, size_t K, int bn,
         if (publishes[b] > 1) ++bad;  // one workspace slot / flag per CTA
         SegIter it(sc.chains_per_tile, sc.full_waves, sc.sk_units, b, sc.grid);
         int tile, c0, c1, skt;
+        // order inside a CTA: the parked segment must be the FIRST phase-2 segment and a finisher segment the LAST one,
+        // otherwise the CTAs serialise (each finisher waiting for a part its predecessor parks at the end of its range)
+        int nseg2 = 0, park_at = -1, finish_at = -1;
+        {
+            SegIter it2(sc.chains_per_tile, sc.full_waves, sc.sk_units, b, sc.grid);
+            while (it2.next(tile, c0, c1, skt)) {
+                if (skt < 0) continue;
+                if (c1 != sc.chains_per_tile) park_at = nseg2;
+                else if (c0 != 0) finish_at = nseg2;
+                ++nseg2;
+            }
+            if (park_at > 0) ++bad;
+            if (finish_at >= 0 && finish_at != nseg2 - 1) ++bad;
+        }
         while (it.next(tile, c0, c1, skt)) {
             if (c1 != sc.chains_per_tile || c0 == 0) continue;
             // finisher: the exact loop of the epilogue warps

@@ -335,6 +335,7 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
         }
         // nobody may exit (and release its shared memory) before rank 0 has read every partial
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        if (split == 0) peer_signal_and_wait(peers);
         return;
     }
     for (int c = tid; c < MROWS * PANEL; c += WARPS * 32) {
@@ -349,7 +350,10 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
         else
             partial[pbase + (size_t)split * N + gc] = s;  // ticket path: MROWS == 1 only (the host never selects it otherwise)
     }
-    if (splits == 1) return;
+    if (splits == 1) {
+        peer_signal_and_wait(peers);
+        return;
+    }
 
     __threadfence();
     __syncthreads();
@@ -372,6 +376,7 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
         store_y(y, gc, s * out_scale, peers);
     }
     if (tid == 0) tickets[batch * gridDim.x + panel] = 0u;  // ready for the next launch
+    peer_signal_and_wait(peers);
 }
 
 }  // namespace b200mm

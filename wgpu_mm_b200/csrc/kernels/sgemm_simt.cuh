@@ -55,7 +55,42 @@ struct PeerStore {
     int rank;      // own rank: its slot in c[] is the local full C
     size_t ldc;    // leading dimension of the full C
     size_t col0;   // first column of this rank's panel in the full C
+    // In-kernel cross-rank completion (b200mm_kernel_set_peer_flags; GEMV kernels): when flags[0] != nullptr the last CTA to
+    // finish publishes `epoch` into slot `rank` of every rank's flag array and waits until all `world` local slots carry
+    // it, so the kernel completes on the stream only when every rank's slice of this step has landed here -- no barrier launch.
+    unsigned int* flags[8];   // flags[d] = rank d's array of >= world + 1 words (own entry = local); word `world` = local CTA counter
+    unsigned int epoch;       // 1, 2, 3, ... per launch
+    unsigned int signal_ctas; // CTAs that store outputs (each bumps the local counter once per launch)
 };
+
+// Called by every thread of a CTA that has issued its last peer stores of the launch.  Returns after the cross-rank
+// wait in the (single) CTA that turned out to be the last one; immediately in all others.
+__device__ __forceinline__ void peer_signal_and_wait(const PeerStore& peers) {
+    if (peers.world <= 1 || peers.flags[0] == nullptr) return;
+    __threadfence_system();  // this thread's stores to the peers are visible system-wide before the CTA is counted
+    __syncthreads();
+    __shared__ unsigned int s_last;
+    unsigned int* local = peers.flags[peers.rank];
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(local + peers.world, 1u);  // monotonic across launches: never reset
+        s_last = (prev + 1u == peers.epoch * peers.signal_ctas) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if ((int)threadIdx.x < peers.world) {
+        const int d = threadIdx.x;
+        __threadfence_system();  // cumulativity: everything the counted CTAs stored is ordered before the flag
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.flags[d] + peers.rank), "r"(peers.epoch) : "memory");
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(local + d) : "memory");
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 10000000000ull) __trap();  // 10 s: a peer never arrived -- fail loudly instead of hanging the GPU
+        } while ((int)(seen - peers.epoch) < 0);
+    }
+}
 
 // Blackwell packed fp32: one FFMA2 performs two IEEE fmas (d.xy = a.xy * b.xy + c.xy).  The outer product is
 // issue-bound (ncu: 78 % issue-active vs 70 % FMA-pipe-active with scalar FFMA), so halving the FMA instruction

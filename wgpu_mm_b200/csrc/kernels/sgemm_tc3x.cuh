@@ -51,15 +51,19 @@ __device__ __forceinline__ float to_tf32_rna(float x) {
 // tools/probe_tc.py), so the raw fp32 operand already acts as hi = trunc(x) and only lo = tf32(x - trunc(x))
 // has to be materialised (x - trunc(x) is exact in fp32).  One launch covers A and B: reads 2 x 64 MB and
 // writes 2 x 64 MB at 4096^3 (a version that also materialised hi wrote 4 x 64 MB).
+__device__ __forceinline__ float split_lo1(float x) { return to_tf32_rna(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); }
+__device__ __forceinline__ float4 split_lo4(const float4& v) { return make_float4(split_lo1(v.x), split_lo1(v.y), split_lo1(v.z), split_lo1(v.w)); }
+
+// Only the first `a4` float4 of A are split here: the rows the first wave of tiles needs.  The remaining row bands of A are
+// split INSIDE sgemm_tc3x_kernel by an otherwise idle warp per CTA while earlier bands are being multiplied (Tc3xArgs::split).
 __global__ void split_lo_kernel(const float4* __restrict__ a, float4* __restrict__ a_lo, size_t a4,
                                 const float4* __restrict__ b, float4* __restrict__ b_lo, size_t b4) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    auto lo1 = [](float x) { return to_tf32_rna(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); };
     for (; i < a4 + b4; i += stride) {
         const bool is_a = i < a4;
         const float4 v = __ldg(is_a ? a + i : b + (i - a4));
-        const float4 l = make_float4(lo1(v.x), lo1(v.y), lo1(v.z), lo1(v.w));
+        const float4 l = split_lo4(v);
         if (is_a)
             a_lo[i] = l;
         else
@@ -214,7 +218,20 @@ struct Tc3xArgs {
     unsigned int* flags;    // [gridDim.x]
     unsigned int epoch;     // bumped by the host on every launch, so flags never need clearing
     PeerStore peers;
+    // In-kernel operand split of A (hides most of the split_lo pass behind the MMAs; at 16384^3 x 8 GPUs the replicated A
+    // made that pass the Amdahl term of the step).  A is cut into bands of kTc3xBandRows rows = the bands of the tile
+    // rasterisation.  Bands [0, prebands) were split by split_lo_kernel before this launch; warp 2 of every CTA splits its
+    // 1/gridDim.x share of bands prebands, prebands + 1, ... in order and then adds 1 to band_cnt[band]; the TMA producer of
+    // a tile in band b >= prebands first waits until band_cnt[b] == epoch * gridDim.x.  Needs all CTAs co-resident
+    // (cooperative launch).  prebands >= number of bands: nothing to do in the kernel.
+    const float* A;
+    float* A_lo;
+    unsigned int* band_cnt;  // [bands], monotonic across launches
+    int prebands;
 };
+
+constexpr int kTc3xGroupM = 16;                     // tile rows per rasterisation band
+constexpr int kTc3xBandRows = kTc3xGroupM * 128;    // rows of A per band
 
 struct SegIter {  // identical iteration in the producer, issuer and epilogue roles (and on the host: b200mm_tc3x_schedule_cover)
     long long u, u1;
@@ -239,13 +256,19 @@ struct SegIter {  // identical iteration in the producer, issuer and epilogue ro
             return true;
         }
         if (u >= u1) return false;
-        sk_tile = (int)(u / cpt);
+        // Phase 2 is walked from the END of the range backwards, segment by segment (chains inside a segment stay ascending):
+        // the segment a CTA has to PARK (the head of a tile that continues in the next CTA) comes first, and the segment it
+        // FINISHES (the tail of a tile begun by preceding CTAs, where it waits for their parts) comes last.  With the forward
+        // order every finisher would wait right away for a part its predecessor only parks at the very end of its range -- the
+        // CTAs would run one after the other.
+        const long long last = u1 - 1;
+        sk_tile = (int)(last / cpt);
         tile = sk_tile0 + sk_tile;
-        c0 = (int)(u % cpt);
-        const long long left = u1 - u;
-        const long long n = (long long)(cpt - c0) < left ? (long long)(cpt - c0) : left;
-        c1 = c0 + (int)n;
-        u += n;
+        const long long tile_start = (long long)sk_tile * cpt;
+        const long long seg_start = u > tile_start ? u : tile_start;
+        c0 = (int)(seg_start - tile_start);
+        c1 = (int)(last - tile_start) + 1;
+        u1 = seg_start;
         return true;
     }
 };
@@ -382,7 +405,7 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     // m-fastest order streams ALL of A through L2 every wave once tiles_m >= 128: measured 193 vs 265 TFLOP/s
     // for 16384^3 vs 4096^3 on one GPU.)
     auto tile_coords = [&](int t, int& tm, int& tn) {
-        constexpr int GROUP_M = 16;
+        constexpr int GROUP_M = kTc3xGroupM;
         const int band_tiles = GROUP_M * p.tiles_n;
         const int band = t / band_tiles;
         const int first_m = band * GROUP_M;
@@ -400,9 +423,23 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
                 uint32_t phase = 0;
                 SegIter it(p);
                 int t, c0, c1, skt;
+                int ready_band = p.prebands - 1;  // bands are completed in order: one high-water mark suffices
                 while (it.next(t, c0, c1, skt)) {
                     int tm, tn;
                     tile_coords(t, tm, tn);
+                    if (!ONE_PASS) {
+                        const int band = tm / kTc3xGroupM;
+                        if (band > ready_band) {
+                            // A_lo of this band is being produced by the splitter warps of ALL CTAs of this launch
+                            const unsigned int target = p.epoch * gridDim.x;
+                            unsigned int seen;
+                            do {
+                                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.band_cnt + band) : "memory");
+                            } while ((int)(seen - target) < 0);
+                            asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy writes -> TMA (async proxy) reads
+                            ready_band = band;
+                        }
+                    }
                     const int kb_end = min(c1 * CHAIN, num_kb);
                     for (int kb = c0 * CHAIN; kb < kb_end; ++kb) {
                         ptx::mbar_wait(empty_bar(stage), phase ^ 1);
@@ -465,6 +502,36 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
                         }
                         ptx::mma_commit(tfull_bar(as));  // chain complete -> epilogue
                     }
+                }
+            }
+        } else if (warp == 2) {
+            // ===================== splitter: A_lo of the later row bands =====================
+            if (!ONE_PASS) {
+                constexpr int U = 16;  // independent 16-byte loads in flight per lane
+                const int bands = (p.M + kTc3xBandRows - 1) / kTc3xBandRows;
+                for (int band = p.prebands; band < bands; ++band) {
+                    const size_t row0 = (size_t)band * kTc3xBandRows;
+                    const size_t rows = min((size_t)kTc3xBandRows, (size_t)p.M - row0);
+                    const size_t n4 = rows * (size_t)p.K / 4;  // K % 4 == 0
+                    const float4* src = reinterpret_cast<const float4*>(p.A + row0 * p.K);
+                    float4* dst = reinterpret_cast<float4*>(p.A_lo + row0 * p.K);
+                    for (size_t base = (size_t)blockIdx.x * (32 * U); base < n4; base += (size_t)gridDim.x * (32 * U)) {
+                        float4 v[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const size_t i = base + (size_t)u * 32 + lane;
+                            if (i < n4) v[u] = __ldcs(src + i);  // streaming: read once here (the GEMM re-reads A through TMA)
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const size_t i = base + (size_t)u * 32 + lane;
+                            if (i < n4) dst[i] = split_lo4(v[u]);
+                        }
+                    }
+                    __threadfence();
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.band_cnt + band) : "memory");
                 }
             }
         } else if (warp == 3 && p.peers.world > 1) {

@@ -128,14 +128,15 @@ class ShardedSgemm:
         ctx.sync()
         dist.barrier()
 
-    def step(self):
+    def step(self, A=None):
         """One full C = A*B on all ranks: every rank holds the complete row-major C when its stream drains."""
+        A = A if A is not None else self.A
         if self.mode == "fused":
-            self.ctx.launch(self.kern, self.A, self.Bp, self.C)
+            self.ctx.launch(self.kern, A, self.Bp, self.C)
             # peer-flag barrier on the same stream: when it completes every rank's tiles of this step have landed here
             self.pbar()
         else:
-            self.ctx.launch(self.kern, self.A, self.Bp, self.Cp)
+            self.ctx.launch(self.kern, A, self.Bp, self.Cp)
             self.dist.all_gather_into_tensor(self.G_t, self.Cp_t)
             self.ctx.unshard_columns(self.G_t.data_ptr(), self.C.ptr, self.M, self.N, self.plan.world)
 
@@ -146,6 +147,13 @@ class ShardedSgemm:
 
     def kernel_times(self):
         return self.kern.profile_read(256)
+
+    def read_rows(self, rows):
+        """Rows of the local copy of the full C (for the out-of-band verification in bench.py / tests)."""
+        out = np.empty((len(rows), self.N), dtype=np.float32)
+        for i, r in enumerate(rows):
+            self.C.read_into(out[i], offset=int(r) * self.N * 4)
+        return out
 
     def checksum(self, rows=(0, 1, 4095)):
         """Sum of a few rows of the local copy of C (consistency across ranks is checked by the caller)."""
@@ -158,38 +166,52 @@ class ShardedSgemm:
         return acc
 
     def e2e(self, steps: int = 2):
-        """The same step through HOST buffers: per step H2D of this rank's inputs (A and its B panel) from pinned
-        memory, the sharded GEMM, and a D2H read of the full C.  Returns seconds per step (max over ranks)."""
+        """The same step through HOST buffers without redundant PCIe traffic: per step this rank uploads only its 1/world
+        row slice of A and its B panel from pinned memory, the slices of A are all-gathered over NVLink (NCCL, in place),
+        the sharded GEMM runs, and the rank reads back only its own column panel of C (the union over the ranks is the
+        full C in host memory, each byte crossing PCIe once).  Returns (seconds per step (max over ranks), H2D bytes,
+        D2H bytes) -- bytes per rank."""
         import ctypes as C
         import time
         w, torch, dist = self.w, self.torch, self.dist
-        M, N, K, Np = self.M, self.N, self.K, self.plan.cols
-        hs = []
-        arrs = []
-        for nfloat in (M * K, K * Np, M * N):
+        M, N, K, Np, g, r = self.M, self.N, self.K, self.plan.cols, self.plan.world, self.plan.rank
+        if M % g:
+            raise ValueError("e2e: M must be a multiple of the world size")
+        Ms = M // g
+        hs, arrs = [], []
+        for nfloat in (Ms * K, K * Np, M * Np):
             h = C.c_void_p()
             w._lib.check(w.lib().b200mm_host_alloc(nfloat * 4, C.byref(h)))
             hs.append(h)
             arrs.append(np.ctypeslib.as_array((C.c_float * nfloat).from_address(h.value)))
         hA, hB, hC = arrs
-        self.A.read_into(hA)
+        self.A.read_into(hA, offset=r * Ms * K * 4)
         self.Bp.read_into(hB)
+        A_t = torch.empty(M * K, dtype=torch.float32, device="cuda")  # gathered A (NCCL needs a torch tensor)
+        A_e = self.ctx.wrap(A_t.data_ptr(), M * K * 4)
+        mine = A_t[r * Ms * K:(r + 1) * Ms * K]
         times = []
         for i in range(steps + 1):
             self.barrier()
             t0 = time.perf_counter()
-            self.A.write(hA)
+            A_e.write(hA, offset=r * Ms * K * 4)
             self.Bp.write(hB)
-            self.step()
-            self.C.read_into(hC)  # blocking: ordered after the step's trailing collective on the same stream
+            dist.all_gather_into_tensor(A_t, mine)  # in place: rank r's slice already sits at its offset
+            self.step(A=A_e)
+            # blocking, ordered after the step's trailing cross-rank barrier on the same stream
+            self.C.read_2d_into(hC, offset=self.plan.col0 * 4, src_pitch=N * 4, width_bytes=Np * 4, rows=M)
             dt = time.perf_counter() - t0
             if i > 0:
                 times.append(dt)
+        self.e2e_panel_checksum = float(hC[:Np].astype(np.float64).sum())
         t = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        self.barrier()
+        A_e.free()
+        del A_t
         for h in hs:
             w.lib().b200mm_host_free(h)
-        return float(t.item()), (M * K + K * Np) * 4, M * N * 4
+        return float(t.item()), (Ms * K + K * Np) * 4, M * Np * 4
 
     def close(self):
         self.barrier()
@@ -206,10 +228,13 @@ class ShardedGemv:
     """y[1 x N] = x[1 x K] * W[K x N] with W (fp32 or sint8 words) cut into `world` column panels (SURVEY 8e:
     "weight rows" in the LLM out x in convention are columns of the reference's K x N matrix, Q3).  x is replicated,
     every rank ends the step holding the full y.  fused: the kernel's final store writes the slice into y on every
-    rank through CUDA-IPC peer mappings; nccl: local slice + all_gather_into_tensor (slices are contiguous)."""
+    rank through CUDA-IPC peer mappings, and the kernel's last CTA publishes a per-step epoch to every rank and waits
+    for theirs (b200mm_kernel_set_peer_flags) -- ONE launch per step, no barrier kernel, no collective.  y is
+    double-buffered by step parity so a fast rank's next step cannot overwrite a y a slower rank still reads.
+    nccl: local slice + all_gather_into_tensor (slices are contiguous)."""
 
     def __init__(self, ctx, K: int, N: int, plan: ShardPlan, quant: bool = False, mode: str = "fused", seed: int = 300,
-                 x_host=None, panel_host=None, absmax: float = 2.0):
+                 x_host=None, panel_host=None, absmax: float = 2.0, nsets: int = 1):
         import torch
         import torch.distributed as dist
         import wgpu_mm_b200 as w
@@ -225,31 +250,43 @@ class ShardedGemv:
         self.x = ctx.buffer_from(x_host) if x_host is not None else ctx.buffer(K * 4)
         if x_host is None:
             self.x.fill_weights(seed + 1, K)
-        if panel_host is not None:
-            self.W = ctx.buffer_from(panel_host)
-        elif quant:
-            self.W = ctx.buffer(K * Np)
-            self.W.fill_weights(seed + 2 + plan.rank, K * Np // 4)  # arbitrary bytes: bandwidth measurements only
-        else:
-            self.W = ctx.buffer(K * Np * 4)
-            self.W.fill_weights_2d(seed + 2, K, Np, N, plan.col0)
-        self.y = ctx.buffer(N * 4)
+        # nsets > 1: that many weight panels, rotated step by step, so that a benchmark loop streams from HBM instead of L2
+        self.Ws = []
+        for i in range(max(1, nsets)):
+            if panel_host is not None:
+                Wb = ctx.buffer_from(panel_host)
+            elif quant:
+                Wb = ctx.buffer(K * Np)
+                Wb.fill_weights(seed + 2 + plan.rank + 1000 * i, K * Np // 4)  # arbitrary bytes: bandwidth measurements only
+            else:
+                Wb = ctx.buffer(K * Np * 4)
+                Wb.fill_weights_2d(seed + 2 + 1000 * i, K, Np, N, plan.col0)
+            self.Ws.append(Wb)
+        self.W, self.steps_done = self.Ws[0], 0
+        self.y = ctx.buffer(2 * N * 4)  # two y buffers, alternated by step parity (fused mode)
         self.peers = []
         kid = w.KernelId.QGEMV_SINT8 if quant else w.KernelId.GEMV_F32
         self.kern = ctx.kernel(kid, 1, Np, K, w.KernelParams(absmax=absmax, batch=1))
         if mode == "fused":
+            self.flags = ctx.buffer(64)
+            self.flags.write(np.zeros(16, dtype=np.uint32))
+            ctx.sync()
             handles = [None] * plan.world
-            dist.all_gather_object(handles, self.y.ipc_export())
-            ptrs = []
+            dist.all_gather_object(handles, (self.y.ipc_export(), self.flags.ipc_export()))
+            ptrs, fptrs = [], []
             for r in range(plan.world):
                 if r == plan.rank:
                     ptrs.append(self.y.ptr)
+                    fptrs.append(self.flags.ptr)
                 else:
-                    pb = ctx.ipc_import(handles[r], N * 4)
-                    self.peers.append(pb)
+                    pb = ctx.ipc_import(handles[r][0], 2 * N * 4)
+                    fb = ctx.ipc_import(handles[r][1], 64)
+                    self.peers += [pb, fb]
                     ptrs.append(pb.ptr)
+                    fptrs.append(fb.ptr)
             self.kern.set_peers(plan.rank, plan.world, ptrs, N, plan.col0)
-            self.pbar = PeerBarrier(ctx, plan)
+            if plan.world > 1:
+                self.kern.set_peer_flags(fptrs, pingpong_stride=N)
         elif mode == "nccl":
             self.ys_t = torch.empty(Np, dtype=torch.float32, device="cuda")
             self.yg_t = torch.empty(N, dtype=torch.float32, device="cuda")
@@ -257,29 +294,30 @@ class ShardedGemv:
             self.yg = ctx.wrap(self.yg_t.data_ptr(), N * 4)
         else:
             raise ValueError(mode)
-        self.kern.profile(True)
         ctx.sync()
         dist.barrier()
 
     def step(self):
+        self.W = self.Ws[self.steps_done % len(self.Ws)]
+        self.steps_done += 1
         if self.mode == "fused":
+            # one launch: when it completes on the stream every rank's y slice of this step has landed here
             self.ctx.launch(self.kern, self.x, self.W, self.y)
-            self.pbar()  # every rank's y slice of this step has landed here when this completes on the stream
         else:
             self.ctx.launch(self.kern, self.x, self.W, self.ys)
             self.dist.all_gather_into_tensor(self.yg_t, self.ys_t)
 
     def result(self) -> np.ndarray:
         self.barrier()
-        return (self.y if self.mode == "fused" else self.yg).read(np.float32, count=self.N)
+        if self.mode != "fused":
+            return self.yg.read(np.float32, count=self.N)
+        parity = self.kern.peer_epoch & 1 if self.plan.world > 1 else 0
+        return self.y.read(np.float32, count=self.N, offset=parity * self.N * 4)
 
     def barrier(self):
         self.ctx.sync()
         self.torch.cuda.synchronize()
         self.dist.barrier()
-
-    def kernel_times(self):
-        return self.kern.profile_read(256)
 
     def bytes_per_rank(self) -> int:
         Np = self.plan.cols
@@ -287,10 +325,10 @@ class ShardedGemv:
 
     def close(self):
         self.barrier()
-        if getattr(self, "pbar", None):
-            self.pbar.close()
         for b in self.peers:
             b.free()
         self.kern.free()
-        for b in (self.x, self.W, self.y):
+        for b in [self.x, self.y] + self.Ws:
             b.free()
+        if getattr(self, "flags", None):
+            self.flags.free()
