@@ -1529,6 +1529,25 @@ extern "C" int b200mm_measure_fma_peak(b200mm_ctx* ctx, int packed, int iters, i
     return B200MM_OK;
 }
 
+// Measurement tool (tools/peer_latency.py): flag ping-pong between two ranks, see peer_pingpong_kernel.  local_flags /
+// peer_flags: one u32 each (IPC-mapped), peer_payload: >= payload floats on the peer.  Returns ns per round trip.
+extern "C" B200MM_API int b200mm_debug_peer_pingpong(b200mm_ctx* ctx, void* local_flag, void* peer_flag, void* peer_payload, int payload,
+                                                     int rank, int iters, int mode, unsigned int base, double* ns_per_round) {
+    if (!ctx || !local_flag || !peer_flag || !ns_per_round || iters <= 0) return fail(ctx, B200MM_ERR_INVALID, "peer_pingpong: bad argument");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    unsigned long long* out = nullptr;
+    CU_TRY(ctx, cudaMalloc(&out, 8));
+    peer_pingpong_kernel<<<1, 256, 0, ctx->stream>>>((unsigned int*)local_flag, (unsigned int*)peer_flag, (float*)peer_payload, payload, rank,
+                                                     iters, mode, base, out);
+    CU_TRY(ctx, cudaGetLastError());
+    unsigned long long ns = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&ns, out, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(out);
+    *ns_per_round = (double)ns / iters;
+    return B200MM_OK;
+}
+
 extern "C" B200MM_API int b200mm_debug_tc_probe(b200mm_ctx* ctx, const void* A, const void* B, size_t M, size_t N, size_t K,
                                                 const uint32_t* u32args /*11*/, void* dumpA, void* dumpB, void* dumpD) {
     if (!ctx || !A || !B) return fail(ctx, B200MM_ERR_INVALID, "probe: NULL argument");
