@@ -619,6 +619,7 @@ def run_multi(args):
                 ctx.timer_begin()
                 for _ in range(nstep):
                     gj.step()  # fused: ONE launch per step (peer stores + in-kernel cross-rank completion), PDL-chained
+                gj.finish()  # the last step's cross-rank completion is inside the timed region
                 gms = ctx.timer_end()
                 gj.barrier()
                 # verification (outside the timed region): own slice vs FP64 from the operands in HBM; full y identical on all ranks

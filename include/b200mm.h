@@ -227,8 +227,14 @@ B200MM_API int b200mm_kernel_set_peers(b200mm_kernel* kern, int rank, int world,
  * must launch the same number of times.  pingpong_stride (floats; 0 = off): successive launches alternate between two y
  * buffers that distance apart (launch e writes y + (e & 1) * stride on every rank; e = b200mm_kernel_peer_epoch after the
  * launch), so a fast rank's step e + 1 never overwrites the y a slower rank's consumer of step e is still reading.
+ * deferred != 0: a launch only PUBLISHES its epoch; the wait for all ranks moves to the start of the NEXT launch of the same
+ * kernel object (after the previous grid has drained, before x is read), so the NVLink flag latency (~3 us one way, measured
+ * with tools/peer_latency.py) hides behind the next launch's ramp-up and weight prefetch -- the form a decode chain wants.
+ * b200mm_kernel_peer_wait then closes the chain: a one-warp kernel on the ctx stream that returns when every rank's last
+ * launch has landed here.
  * peer_flags == NULL switches back to caller-side synchronisation. */
-B200MM_API int b200mm_kernel_set_peer_flags(b200mm_kernel* kern, void* const* peer_flags, size_t pingpong_stride);
+B200MM_API int b200mm_kernel_set_peer_flags(b200mm_kernel* kern, void* const* peer_flags, size_t pingpong_stride, int deferred);
+B200MM_API int b200mm_kernel_peer_wait(b200mm_ctx* ctx, b200mm_kernel* kern);
 B200MM_API unsigned int b200mm_kernel_peer_epoch(const b200mm_kernel* kern);
 /* Stream-ordered barrier across the ranks of one box without a collective library: `local_flags` is a
  * library-allocated, zero-initialised buffer of >= world u32 on every rank, `peer_flags[r]` its mapping on

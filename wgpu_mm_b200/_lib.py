@@ -149,7 +149,8 @@ def _declare(l: C.CDLL) -> None:
     l.b200mm_ipc_export.argtypes = [vp, vp, vp]
     l.b200mm_ipc_import.argtypes = [vp, vp, sz, C.POINTER(vp)]
     l.b200mm_kernel_set_peers.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), sz, sz]
-    l.b200mm_kernel_set_peer_flags.argtypes = [vp, C.POINTER(vp), sz]
+    l.b200mm_kernel_set_peer_flags.argtypes = [vp, C.POINTER(vp), sz, C.c_int]
+    l.b200mm_kernel_peer_wait.argtypes = [vp, vp]
     l.b200mm_kernel_peer_epoch.argtypes = [vp]
     l.b200mm_kernel_peer_epoch.restype = C.c_uint
     l.b200mm_peer_barrier.argtypes = [vp, vp, C.POINTER(vp), C.c_int, C.c_int]

@@ -231,10 +231,14 @@ class Kernel:
         arr = (C.c_void_p * max(world, 1))(*[C.c_void_p(p) for p in peer_ptrs])
         check(lib().b200mm_kernel_set_peers(self._h, rank, world, arr, ldc, col_offset))
 
-    def set_peer_flags(self, peer_ptrs: Optional[Sequence[int]], pingpong_stride: int = 0):
+    def set_peer_flags(self, peer_ptrs: Optional[Sequence[int]], pingpong_stride: int = 0, deferred: bool = False):
         """In-kernel cross-rank completion (GEMV): see b200mm_kernel_set_peer_flags."""
         arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(p) for p in peer_ptrs]) if peer_ptrs else None
-        check(lib().b200mm_kernel_set_peer_flags(self._h, arr, pingpong_stride))
+        check(lib().b200mm_kernel_set_peer_flags(self._h, arr, pingpong_stride, 1 if deferred else 0))
+
+    def peer_wait(self):
+        """Closes a chain of deferred launches: stream-ordered wait until every rank's last launch has landed here."""
+        check(lib().b200mm_kernel_peer_wait(self.ctx.handle, self._h), self.ctx.handle)
 
     @property
     def peer_epoch(self) -> int:

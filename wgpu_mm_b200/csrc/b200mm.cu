@@ -987,12 +987,13 @@ extern "C" int b200mm_kernel_set_peers(b200mm_kernel* k, int rank, int world, vo
     return B200MM_OK;
 }
 
-extern "C" int b200mm_kernel_set_peer_flags(b200mm_kernel* k, void* const* peer_flags, size_t pingpong_stride) {
+extern "C" int b200mm_kernel_set_peer_flags(b200mm_kernel* k, void* const* peer_flags, size_t pingpong_stride, int deferred) {
     if (!k) return fail(nullptr, B200MM_ERR_INVALID, "set_peer_flags: kern is NULL");
     if (k->id != B200MM_K_GEMV_F32 && k->id != B200MM_K_QGEMV_SINT8)
         return fail(nullptr, B200MM_ERR_INVALID, "set_peer_flags: only the streaming GEMV kernels complete across ranks in-kernel");
     if (k->peers.world < 2) return fail(nullptr, B200MM_ERR_INVALID, "set_peer_flags: call b200mm_kernel_set_peers first (world >= 2)");
     for (int i = 0; i < 8; ++i) k->peers.flags[i] = nullptr;
+    k->peers.deferred = 0;
     k->peer_epoch = 0;
     k->peer_pingpong = 0;
     if (!peer_flags) return B200MM_OK;  // back to "caller synchronises the ranks" (b200mm_peer_barrier / a collective)
@@ -1001,6 +1002,18 @@ extern "C" int b200mm_kernel_set_peer_flags(b200mm_kernel* k, void* const* peer_
         k->peers.flags[i] = (unsigned int*)peer_flags[i];
     }
     k->peer_pingpong = pingpong_stride;
+    k->peers.deferred = deferred ? 1u : 0u;
+    return B200MM_OK;
+}
+
+extern "C" int b200mm_kernel_peer_wait(b200mm_ctx* ctx, b200mm_kernel* k) {
+    if (!ctx || !k) return fail(ctx, B200MM_ERR_INVALID, "peer_wait: NULL argument");
+    if (k->peers.world < 2 || !k->peers.flags[0]) return fail(ctx, B200MM_ERR_INVALID, "peer_wait: no peer flags set on this kernel");
+    if (k->peer_epoch == 0) return B200MM_OK;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(k->peers, k->peer_epoch);
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
     return B200MM_OK;
 }
 

@@ -158,6 +158,11 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
         }
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    // N-sharded chain with deferred completion: x may derive from the y the peers stored during the PREVIOUS launch
+    if (peers.world > 1 && peers.flags[0] != nullptr && peers.deferred && peers.epoch > 1) {
+        peer_wait_epoch(peers, peers.epoch - 1);
+        __syncthreads();
+    }
 
     // x -> shared memory with 128-bit loads (K % 4 == 0, splits start on multiples of 4): this sits between the PDL wait and the
     // first FMA, so a scalar strided loop (rows_per_split / threads dependent L2 round trips) was ~1 us of a ~12 us kernel

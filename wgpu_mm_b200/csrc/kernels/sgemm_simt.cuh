@@ -61,7 +61,27 @@ struct PeerStore {
     unsigned int* flags[8];   // flags[d] = rank d's array of >= world + 1 words (own entry = local); word `world` = local CTA counter
     unsigned int epoch;       // 1, 2, 3, ... per launch
     unsigned int signal_ctas; // CTAs that store outputs (each bumps the local counter once per launch)
+    unsigned int deferred;    // 0: the last CTA also WAITS for every rank's epoch before the kernel ends (kernel completion =>
+                              //    all slices have landed here).  1: it only publishes; the NEXT launch of the kernel object waits
+                              //    for epoch - 1 right after griddepcontrol.wait, before it touches x, so the NVLink latency hides
+                              //    behind the next launch's ramp-up and weight prefetch (b200mm_kernel_peer_wait closes a chain).
 };
+
+// every rank has published `epoch` into the local flag array (threads 0 .. world-1 poll one slot each)
+__device__ __forceinline__ void peer_wait_epoch(const PeerStore& peers, unsigned int epoch) {
+    if ((int)threadIdx.x < peers.world) {
+        const unsigned int* local = peers.flags[peers.rank];
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(local + threadIdx.x) : "memory");
+            if ((int)(seen - epoch) >= 0) break;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 10000000000ull) __trap();  // 10 s: a peer never arrived -- fail loudly instead of hanging the GPU
+        } while (true);
+    }
+}
 
 // Called by every thread of a CTA that has issued its last peer stores of the launch.  Returns after the cross-rank
 // wait in the (single) CTA that turned out to be the last one; immediately in all others.
@@ -81,16 +101,12 @@ __device__ __forceinline__ void peer_signal_and_wait(const PeerStore& peers) {
         const int d = threadIdx.x;
         __threadfence_system();  // cumulativity: everything the counted CTAs stored is ordered before the flag
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.flags[d] + peers.rank), "r"(peers.epoch) : "memory");
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
-        unsigned int seen;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(local + d) : "memory");
-            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 10000000000ull) __trap();  // 10 s: a peer never arrived -- fail loudly instead of hanging the GPU
-        } while ((int)(seen - peers.epoch) < 0);
     }
+    if (!peers.deferred) peer_wait_epoch(peers, peers.epoch);
 }
+
+// Closes a chain of deferred launches: one warp waits until every rank has published `epoch`.
+__global__ void peer_wait_kernel(PeerStore peers, unsigned int epoch) { peer_wait_epoch(peers, epoch); }
 
 // Blackwell packed fp32: one FFMA2 performs two IEEE fmas (d.xy = a.xy * b.xy + c.xy).  The outer product is
 // issue-bound (ncu: 78 % issue-active vs 70 % FMA-pipe-active with scalar FFMA), so halving the FMA instruction

@@ -229,12 +229,14 @@ class ShardedGemv:
     "weight rows" in the LLM out x in convention are columns of the reference's K x N matrix, Q3).  x is replicated,
     every rank ends the step holding the full y.  fused: the kernel's final store writes the slice into y on every
     rank through CUDA-IPC peer mappings, and the kernel's last CTA publishes a per-step epoch to every rank and waits
-    for theirs (b200mm_kernel_set_peer_flags) -- ONE launch per step, no barrier kernel, no collective.  y is
+    for theirs (b200mm_kernel_set_peer_flags) -- ONE launch per step, no barrier kernel, no collective.  By default the
+    wait is DEFERRED to the start of the next step's launch (a decode chain: x of step i+1 derives from y of step i), so
+    the NVLink flag latency hides behind that launch's ramp-up; finish() closes the chain.  y is
     double-buffered by step parity so a fast rank's next step cannot overwrite a y a slower rank still reads.
     nccl: local slice + all_gather_into_tensor (slices are contiguous)."""
 
     def __init__(self, ctx, K: int, N: int, plan: ShardPlan, quant: bool = False, mode: str = "fused", seed: int = 300,
-                 x_host=None, panel_host=None, absmax: float = 2.0, nsets: int = 1):
+                 x_host=None, panel_host=None, absmax: float = 2.0, nsets: int = 1, deferred: bool = True):
         import torch
         import torch.distributed as dist
         import wgpu_mm_b200 as w
@@ -285,8 +287,9 @@ class ShardedGemv:
                     ptrs.append(pb.ptr)
                     fptrs.append(fb.ptr)
             self.kern.set_peers(plan.rank, plan.world, ptrs, N, plan.col0)
+            self.deferred = deferred and plan.world > 1
             if plan.world > 1:
-                self.kern.set_peer_flags(fptrs, pingpong_stride=N)
+                self.kern.set_peer_flags(fptrs, pingpong_stride=N, deferred=deferred)
         elif mode == "nccl":
             self.ys_t = torch.empty(Np, dtype=torch.float32, device="cuda")
             self.yg_t = torch.empty(N, dtype=torch.float32, device="cuda")
@@ -307,7 +310,13 @@ class ShardedGemv:
             self.ctx.launch(self.kern, self.x, self.W, self.ys)
             self.dist.all_gather_into_tensor(self.yg_t, self.ys_t)
 
+    def finish(self):
+        """Closes a chain of steps on the stream: afterwards the full y of the last step is complete on this rank."""
+        if self.mode == "fused" and getattr(self, "deferred", False):
+            self.kern.peer_wait()
+
     def result(self) -> np.ndarray:
+        self.finish()
         self.barrier()
         if self.mode != "fused":
             return self.yg.read(np.float32, count=self.N)
