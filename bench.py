@@ -536,6 +536,10 @@ def run_multi(args):
     from wgpu_mm_b200 import shard
 
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    # NCCL prints its version banner on stdout; the contract is ONE JSON line there, so everything else goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks = load_peaks()
@@ -682,7 +686,10 @@ def run_multi(args):
                     if e2e_s else None),
             "gpu_launches": int(launches), "clocks": clocks, "ranks_hold_identical_c": bool(consistent), "extras": extras,
         }
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     ctx.close()
     dist.destroy_process_group()
 

@@ -25,8 +25,11 @@ def main():
         plan = shard.ShardPlan(N, world, rank)
         pbytes = K * plan.cols * (1 if quant else 4)
         nsets = int(min(32, max(2, -(-(160 << 20) // pbytes))))
-        for mode, deferred in (("fused", False), ("fused", True), ("nccl", False)):
-            gj = shard.ShardedGemv(ctx, K, N, plan, quant=quant, mode=mode, nsets=nsets, deferred=deferred)
+        for mode, deferred in (("fused", False), ("fused", True), ("fused-nosync", False), ("nccl", False)):
+            gj = shard.ShardedGemv(ctx, K, N, plan, quant=quant, mode=mode.split("-")[0], nsets=nsets, deferred=deferred)
+            if mode == "fused-nosync":  # peer stores only, no cross-rank completion: NOT a valid step, isolates the cost of the stores
+                gj.kern.set_peer_flags(None)
+                gj.deferred = False
             for _ in range(20):
                 gj.step()
             gj.finish(); gj.barrier()

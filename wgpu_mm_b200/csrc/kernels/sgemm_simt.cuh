@@ -87,12 +87,17 @@ __device__ __forceinline__ void peer_wait_epoch(const PeerStore& peers, unsigned
 // wait in the (single) CTA that turned out to be the last one; immediately in all others.
 __device__ __forceinline__ void peer_signal_and_wait(const PeerStore& peers) {
     if (peers.world <= 1 || peers.flags[0] == nullptr) return;
-    __threadfence_system();  // this thread's stores to the peers are visible system-wide before the CTA is counted
+    // Ordering without a system-scope fence per thread (hundreds of concurrent MEMBAR.SYS serialise device-wide: measured
+    // +15 us per launch): the CTA's stores -> bar.sync -> thread 0: gpu-scope fence + counter (release pattern); the last
+    // CTA's thread 0 reads the counter + gpu-scope fence (acquire pattern) -> bar.sync -> ONE sys-scope release per peer.
+    // Causality order is transitive across these scopes, so every counted store is visible before the flag.
     __syncthreads();
     __shared__ unsigned int s_last;
     unsigned int* local = peers.flags[peers.rank];
     if (threadIdx.x == 0) {
+        __threadfence();
         const unsigned int prev = atomicAdd(local + peers.world, 1u);  // monotonic across launches: never reset
+        __threadfence();
         s_last = (prev + 1u == peers.epoch * peers.signal_ctas) ? 1u : 0u;
     }
     __syncthreads();
