@@ -70,8 +70,8 @@ typedef enum b200mm_kernel_id {
 
     B200MM_K_SGEMM_SIMT = 32, /* warp-tiled FP32 FMA-pipe SGEMM (gemm_5's idea, B200 sized)   */
     B200MM_K_SGEMM_TC3X = 33, /* TMA + tcgen05/TMEM SGEMM, 3xTF32 split (FP32-accurate)       */
-    B200MM_K_GEMV_F32 = 34,   /* HBM-streaming fp32 GEMV; M in {1,2,4,8} rows of x share one pass over W */
-    B200MM_K_QGEMV_SINT8 = 35 /* HBM-streaming sint8 GEMV, in-register dequant; M in {1,2,4}             */
+    B200MM_K_GEMV_F32 = 34,   /* HBM-streaming fp32 GEMV; M <= 16 rows of x (1, 2, 4, 8 share one pass over W; other counts run in such chunks) */
+    B200MM_K_QGEMV_SINT8 = 35 /* HBM-streaming sint8 GEMV, in-register dequant; M <= 16 (chunks of 4, 2, 1 rows)                        */
 } b200mm_kernel_id;
 
 /* Replaces what the reference bakes into the WGSL text through Tera (src/gemm.rs:24-29,

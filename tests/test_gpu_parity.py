@@ -113,9 +113,11 @@ def test_sgemm_tc3x(gpu_ctx, oracle, shape, bn):
     _check(oracle, got, A, B)
 
 
-@pytest.mark.parametrize("shape", [(100, 36, 20), (129, 260, 36), (500, 1000, 252), (128, 4, 4)])
+@pytest.mark.parametrize("shape", [(100, 36, 20), (129, 260, 36), (500, 1000, 252), (128, 4, 4), (128, 130, 66), (48, 4096, 4096), (1, 7, 5),
+                                   (100, 37, 21), (257, 1001, 515), (300, 64, 1027), (13, 14336, 4096)])
 def test_sgemm_tc3x_ragged(gpu_ctx, oracle, shape):
-    """TMA zero-fills out-of-range rows / k; the epilogue guards the stores (needs N%4 == K%4 == 0)."""
+    """TMA zero-fills out-of-range rows / k and the epilogue guards the stores; N or K not a multiple of 4 goes through
+    zero-padded staging copies (arbitrary M, N, K on the tensor-core path)."""
     import wgpu_mm_b200 as w
     M, N, K = shape
     A = oracle.generate_weight_data(11, M, K)
@@ -176,10 +178,24 @@ def test_split_k_fixup_survives_a_busy_device(gpu_ctx, oracle, kid_name):
     hog.free(); kern.free(); other.close()
 
 
-def test_sgemm_tc3x_rejects_unaligned(gpu_ctx):
+def test_sgemm_tc3x_padded_path_is_deterministic_and_leaves_neighbours_alone(gpu_ctx, oracle):
+    """N % 4 != 0: C has an odd pitch; the copy-back must write exactly M x N floats (canary behind C) and repeat bit for bit."""
     import wgpu_mm_b200 as w
-    with pytest.raises(w.B200mmError):
-        gpu_ctx.kernel(w.KernelId.SGEMM_TC3X, 128, 130, 64)
+    M, N, K = 70, 130, 66
+    A = oracle.generate_weight_data(17, M, K)
+    B = oracle.generate_weight_data(18, K, N)
+    kern = gpu_ctx.kernel(w.KernelId.SGEMM_TC3X, M, N, K)
+    dA, dB = gpu_ctx.buffer_from(A), gpu_ctx.buffer_from(B)
+    dC = gpu_ctx.buffer_from(np.full(M * N + 64, 7.0, dtype=np.float32))
+    gpu_ctx.launch(kern, dA, dB, dC)
+    first = dC.read(np.float32)
+    gpu_ctx.launch(kern, dA, dB, dC)
+    second = dC.read(np.float32)
+    assert (first[M * N:] == 7.0).all() and np.array_equal(first, second)
+    _check(oracle, first[:M * N].reshape(M, N), A, B)
+    for b in (dA, dB, dC):
+        b.free()
+    kern.free()
 
 
 def test_sgemm_tc3x_single_pass_fails_the_gate_at_large_k(gpu_ctx, oracle):
@@ -536,7 +552,7 @@ def test_gemv_dependent_chain_with_pdl(gpu_ctx, oracle, quant):
     kern.free()
 
 
-@pytest.mark.parametrize("m", [2, 4, 8])
+@pytest.mark.parametrize("m", [2, 3, 4, 5, 7, 8, 13, 16])
 @pytest.mark.parametrize("kn", [(512, 1024), (4096, 4096), (1000, 260)])
 def test_gemv_f32_skinny_m(gpu_ctx, oracle, m, kn):
     """Skinny GEMM: M rows of x share one pass over W; semantics = mm_ref with M rows."""
@@ -548,10 +564,14 @@ def test_gemv_f32_skinny_m(gpu_ctx, oracle, m, kn):
     _check(oracle, got, X, W)
 
 
-@pytest.mark.parametrize("m", [2, 4])
-def test_qgemv_sint8_skinny_m(gpu_ctx, oracle, m):
+@pytest.mark.parametrize("kn", [(1024, 2048), (4096, 14336)])
+@pytest.mark.parametrize("m", [2, 3, 4, 6, 13, 16])
+def test_qgemv_sint8_skinny_m(gpu_ctx, oracle, m, kn):
+    """Every M <= 16: row counts without an instantiation of their own run in chunks of 4 / 2 / 1 rows."""
     import wgpu_mm_b200 as w
-    K, N = 1024, 2048
+    K, N = kn
+    if (K, N) == (4096, 14336) and m not in (3, 13):
+        pytest.skip("BASELINE shape: the ragged row counts only")
     X = oracle.generate_weight_data(63, m, K)
     W = oracle.generate_weight_data(64, K, N)
     words, _ = oracle.sint8_quantize(W, K, N)
@@ -563,11 +583,17 @@ def test_qgemv_sint8_skinny_m(gpu_ctx, oracle, m):
 
 
 def test_gemv_rejects_unsupported_m(gpu_ctx):
+    """The GEMV kernels stop at 16 rows of x (above that the SGEMM kernels take over); batched / grouped / peer-store launches
+    keep to the natively instantiated row counts."""
     import wgpu_mm_b200 as w
     with pytest.raises(w.B200mmError):
-        gpu_ctx.kernel(w.KernelId.GEMV_F32, 3, 1024, 1024)
+        gpu_ctx.kernel(w.KernelId.GEMV_F32, 17, 1024, 1024)
     with pytest.raises(w.B200mmError):
-        gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 8, 1024, 1024, w.KernelParams(absmax=2.0))
+        gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 17, 1024, 1024, w.KernelParams(absmax=2.0))
+    with pytest.raises(w.B200mmError):
+        gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 3, 1024, 1024, w.KernelParams(absmax=2.0, batch=2))
+    with pytest.raises(w.B200mmError):
+        gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 3, 1024, 1024, w.KernelParams(group_k=128))
 
 
 @pytest.mark.parametrize("case", ["gemv_f32", "qgemv_sint8", "gemv_f32_m4", "sgemm_tc3x", "sgemm_simt"])

@@ -91,6 +91,18 @@ struct b200mm_kernel {
     b200mm_kernel* panel = nullptr;
     int panel_count = 0;
     bool tc_skip_b_split = false;  // B's lo part in the workspace is still valid (same B, pipelined panels)
+    // skinny GEMM on the GEMV kernels for row counts that have no instantiation of their own (M = 3, 5, 6, 7, 9 .. 16): the
+    // rows are cut into chunks that do (8 / 4 / 2 / 1), one child kernel object per chunk, launched back to back
+    struct RowChunk {
+        b200mm_kernel* kern;
+        size_t row0;
+    };
+    std::vector<RowChunk> chunks;
+    // sgemm_tc3x with N % 4 != 0 or K % 4 != 0: operands are staged into zero-padded copies (16-byte TMA strides) and the
+    // padded result is copied back; `inner` is the kernel object of the padded shape (owned)
+    b200mm_kernel* inner = nullptr;
+    float *pad_a = nullptr, *pad_b = nullptr, *pad_c = nullptr;
+    size_t pad_k = 0, pad_n = 0;
     // per-launch profiling of the dominant kernel
     bool profiling = false;
     std::vector<cudaEvent_t> pev;  // pairs
@@ -591,8 +603,28 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     const size_t M = k->M, N = k->N, K = k->K;
     if (ctx->prop.major != 10)
         return fail(ctx, B200MM_ERR_UNSUPPORTED, "sgemm_tc3x needs an sm_100 device (got sm_%d%d)", ctx->prop.major, ctx->prop.minor);
-    if (N % 4 || K % 4) return fail(ctx, B200MM_ERR_INVALID, "sgemm_tc3x needs N%%4==0 and K%%4==0 (TMA 16-byte strides)");
     if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return fail(ctx, B200MM_ERR_INVALID, "shape too large");
+    if (N % 4 || K % 4) {
+        // TMA needs 16-byte row strides and the epilogue stores float4: run the padded shape (K -> K4, N -> N4, zero fill) on
+        // staged copies.  An edge path: three extra HBM passes over the operands, O(MK + KN + MN).
+        if (k->prm.flags & B200MM_F_PEER_STORE) return fail(ctx, B200MM_ERR_INVALID, "sgemm_tc3x: peer stores need N%%4==0 and K%%4==0");
+        k->pad_k = ceil_div(K, 4) * 4;
+        k->pad_n = ceil_div(N, 4) * 4;
+        b200mm_kernel_params prm = k->prm;
+        int rc = b200mm_kernel_get(ctx, B200MM_K_SGEMM_TC3X, M, k->pad_n, k->pad_k, &prm, &k->inner);
+        if (rc) return rc;
+        const size_t ab = M * k->pad_k * 4, bb = k->pad_k * k->pad_n * 4, cb = M * k->pad_n * 4;
+        const size_t al = ceil_div(ab, 256) * 256, bl = ceil_div(bb, 256) * 256;
+        k->ws_bytes = al + bl + cb;
+        CU_TRY(ctx, cudaMalloc(&k->ws, k->ws_bytes));
+        CU_TRY(ctx, cudaMemsetAsync(k->ws, 0, k->ws_bytes, ctx->stream));  // the pad columns / rows stay zero for ever
+        k->pad_a = (float*)k->ws;
+        k->pad_b = (float*)((char*)k->ws + al);
+        k->pad_c = (float*)((char*)k->ws + al + bl);
+        k->grid = k->inner->grid;
+        k->block = k->inner->block;
+        return B200MM_OK;
+    }
     const bool one_pass = (k->prm.flags & B200MM_F_TC3X_1X) != 0;
     k->tc_bn = (k->prm.tune[0] == 128) ? 128 : 256;
     k->tc_bk = (k->prm.tune[2] == 32) ? 32 : 16;  // default: BK = 16, 4 stages
@@ -668,9 +700,31 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
 static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     const size_t M = k->M, N = k->N, K = k->K;
     const int cols = quant ? 16 : 4;
-    if (M != 1 && M != 2 && M != 4 && !(M == 8 && !quant))
-        return fail(ctx, B200MM_ERR_INVALID, "%s takes M in {1, 2, 4%s} rows of x (skinny GEMM); use an SGEMM kernel for larger M", b200mm_kernel_name(k->id),
-                    quant ? "" : ", 8");
+    if (M > 16)
+        return fail(ctx, B200MM_ERR_INVALID, "%s takes M <= 16 rows of x (skinny GEMM); use an SGEMM kernel for larger M", b200mm_kernel_name(k->id));
+    if (M != 1 && M != 2 && M != 4 && !(M == 8 && !quant)) {
+        // no instantiation for this row count: chunks of 8 / 4 / 2 / 1 rows, each one pass over W (a second pass over a
+        // sint8 matrix of the BASELINE size is served from L2)
+        if (k->prm.batch > 1) return fail(ctx, B200MM_ERR_INVALID, "%s: batch > 1 needs M in {1, 2, 4%s}", b200mm_kernel_name(k->id), quant ? "" : ", 8");
+        if (k->prm.group_k) return fail(ctx, B200MM_ERR_INVALID, "qgemv_sint8 with group_k: M must be 1");
+        if (k->prm.flags & B200MM_F_PEER_STORE) return fail(ctx, B200MM_ERR_INVALID, "%s: peer stores need M == 1", b200mm_kernel_name(k->id));
+        size_t row0 = 0;
+        for (size_t c : {(size_t)8, (size_t)4, (size_t)2, (size_t)1}) {
+            if (c == 8 && quant) continue;
+            while (M - row0 >= c) {
+                b200mm_kernel* child = nullptr;
+                b200mm_kernel_params prm = k->prm;
+                prm.flags &= ~B200MM_F_AUTOTUNE;
+                int rc = b200mm_kernel_get(ctx, k->id, c, N, K, &prm, &child);
+                if (rc) return rc;
+                k->chunks.push_back({child, row0});
+                row0 += c;
+            }
+        }
+        k->grid = k->chunks[0].kern->grid;
+        k->block = k->chunks[0].kern->block;
+        return B200MM_OK;
+    }
     const int mrows = (int)M;
     if (N % cols || K % 4)
         return fail(ctx, B200MM_ERR_INVALID, "%s needs N%%%d==0 and K%%4==0", b200mm_kernel_name(k->id), cols);
@@ -909,6 +963,8 @@ extern "C" int b200mm_kernel_get(b200mm_ctx* ctx, int kernel_id, size_t M, size_
     else
         rc = fail(ctx, B200MM_ERR_UNSUPPORTED, "unknown kernel id %d", kernel_id);
     if (rc) {
+        if (k->inner) b200mm_kernel_free(ctx, k->inner);
+        for (auto& c : k->chunks) b200mm_kernel_free(ctx, c.kern);
         if (k->ws) cudaFree(k->ws);
         delete k;
         return rc;
@@ -924,6 +980,8 @@ extern "C" int b200mm_kernel_free(b200mm_ctx* ctx, b200mm_kernel* kern) {
         cudaStreamSynchronize(ctx->stream);
     }
     if (kern->panel) b200mm_kernel_free(ctx, kern->panel);
+    if (kern->inner) b200mm_kernel_free(ctx, kern->inner);
+    for (auto& c : kern->chunks) b200mm_kernel_free(ctx, c.kern);
     if (kern->ws) cudaFree(kern->ws);
     for (auto e : kern->pev) cudaEventDestroy(e);
     delete kern;
@@ -1074,6 +1132,22 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
     const float* Af = (const float*)A;
     const float* Bf = (const float*)B;
     float* Cf = (float*)C;
+    if (!k->chunks.empty()) {  // skinny GEMM in row chunks (see b200mm_kernel::chunks)
+        for (auto& c : k->chunks) {
+            int rc = b200mm_launch_ptr(ctx, c.kern, Af + c.row0 * k->K, B, Cf + c.row0 * k->N, nullptr);
+            if (rc) return rc;
+        }
+        return B200MM_OK;
+    }
+    if (k->inner) {  // ragged N / K through zero-padded staging copies (see b200mm_kernel::inner)
+        const size_t Kp = k->pad_k, Np = k->pad_n;
+        CU_TRY(ctx, cudaMemcpy2DAsync(k->pad_a, Kp * 4, A, k->K * 4, k->K * 4, k->M, cudaMemcpyDeviceToDevice, s));
+        CU_TRY(ctx, cudaMemcpy2DAsync(k->pad_b, Np * 4, B, k->N * 4, k->N * 4, k->K, cudaMemcpyDeviceToDevice, s));
+        int rc = b200mm_launch_ptr(ctx, k->inner, k->pad_a, k->pad_b, k->pad_c, nullptr);
+        if (rc) return rc;
+        CU_TRY(ctx, cudaMemcpy2DAsync(C, k->N * 4, k->pad_c, Np * 4, k->N * 4, k->M, cudaMemcpyDeviceToDevice, s));
+        return B200MM_OK;
+    }
     const int pslot = k->pcount % kProfRing;
     auto prof_begin = [&]() {
         if (k->profiling) cudaEventRecord(k->pev[2 * pslot], s);
@@ -1277,6 +1351,8 @@ extern "C" int b200mm_mm_host(b200mm_ctx* ctx, b200mm_kernel* kern, const void* 
     }
     if (!kern->panel || kern->panel_count != P) {
         if (kern->panel) b200mm_kernel_free(ctx, kern->panel);
+    if (kern->inner) b200mm_kernel_free(ctx, kern->inner);
+    for (auto& c : kern->chunks) b200mm_kernel_free(ctx, c.kern);
         kern->panel = nullptr;
         b200mm_kernel_params prm = kern->prm;
         if ((rc = b200mm_kernel_get(ctx, kern->id, M / P, N, K, &prm, &kern->panel))) return rc;
