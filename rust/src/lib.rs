@@ -1,11 +1,22 @@
-//! Crate root as it would look with the B200 back-end (UNCOMPILED here: no Rust toolchain in the build image).
-//! `workload.rs` and `quant.rs` are used from the upstream crate unchanged and are deliberately not duplicated in
-//! this repository; `gemm.rs` / `gemv.rs` keep their public signatures (see entry_points.rs); `harness.rs` swaps
-//! its five wgpu touch-points for the C ABI (see harness_patch.rs).
+//! Crate root with the B200 back-end.  UNCOMPILED in this repository (no Rust toolchain in the build image); kept in step with
+//! the C headers by tests/test_host.py::test_rust_shim_binds_every_exported_symbol.
+//!
+//! Public surface = upstream `src/lib.rs:1-10`: `gemm`, `gemv`, `quant` modules, and `test_harness`, `Workload`,
+//! `WorkgroupCount`, `WorkgroupSize`, `WorkloadDim` re-exported at the root.  What changed underneath:
+//!   * `wgpu` (device, buffers, pipeline, dispatch, read-back)  ->  `ffi` over libb200mm.so, wrapped by `device`;
+//!   * `tera` (WGSL templating)  ->  `tera` below, a two-type stand-in so the entry points keep their signatures
+//!     `fn(&mut Tera, &mut Context) -> (Workload, String)`; the `String` is now a kernel name, not WGSL text;
+//!   * `rand`  ->  a seeded counter generator (bit-identical to the CUDA-side generator, so 16384^2 operands can also be
+//!     produced on the device).
 #![allow(non_snake_case)]
-pub mod entry_points; // gemm::{insert_matrix_dims, gemm_1..gemm_5}, gemv::{ABSMAX, insert_matrix_dims, qgemv_1}
+pub mod device;
 pub mod ffi;
-mod harness_patch;
-// pub mod quant;     // upstream src/quant.rs, unchanged
-// mod workload;      // upstream src/workload.rs, unchanged
-pub use harness_patch::*;
+pub mod gemm;
+pub mod gemv;
+mod harness;
+mod launch_shape;
+pub mod quant;
+pub mod tera;
+
+pub use harness::*;
+pub use launch_shape::*;
