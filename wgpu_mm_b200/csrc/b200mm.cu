@@ -85,6 +85,8 @@ struct b200mm_kernel {
     int simt_tiles1 = 0, simt_tiles2 = 0;
     // multi-GPU
     PeerStore peers{};
+    unsigned long long* trace_buf = nullptr;  // debug timeline of the GEMV kernels (b200mm_debug_gemv_trace)
+    int trace_slots = 0, trace_next = 0;
     unsigned int peer_epoch = 0;   // launches since set_peer_flags (in-kernel cross-rank completion)
     size_t peer_pingpong = 0;      // GEMV: distance (floats) between the two y buffers alternated by epoch parity; 0 = one buffer
     // row-panel kernel object used by the pipelined host-buffer path (owned)
@@ -1274,8 +1276,15 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
                 ps.signal_ctas = (unsigned)k->panels;  // one storing CTA per column panel (batch == 1 with peers)
                 ps.col0 += (size_t)(ps.epoch & 1u) * k->peer_pingpong;
             }
-            CU_TRY(ctx, cudaLaunchKernelEx(&cfg, fn, Af, (const void*)B, Cf, k->partial, k->tickets, (int)K, (int)N, k->rows_per_split, scale,
-                                           (size_t)k->M * K, wstride, (size_t)k->M * N, ps, cluster ? 1 : 0, (int)group_k));
+            int cluster_arg = cluster ? 1 : 0;
+            unsigned int* tickets = k->tickets;
+            if (k->trace_buf && (cluster || k->splits == 1)) {  // the ticket path needs `tickets` itself
+                cluster_arg |= (k->trace_next % k->trace_slots + 1) << 8;
+                k->trace_next++;
+                tickets = (unsigned int*)k->trace_buf;
+            }
+            CU_TRY(ctx, cudaLaunchKernelEx(&cfg, fn, Af, (const void*)B, Cf, k->partial, tickets, (int)K, (int)N, k->rows_per_split, scale,
+                                           (size_t)k->M * K, wstride, (size_t)k->M * N, ps, cluster_arg, (int)group_k));
             break;
         }
         default:
@@ -1634,6 +1643,16 @@ extern "C" B200MM_API int b200mm_debug_peer_pingpong(b200mm_ctx* ctx, void* loca
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(out);
     *ns_per_round = (double)ns / iters;
+    return B200MM_OK;
+}
+
+// Debug (tools/trace_gemv.py): per-CTA globaltimer stamps of the next `slots` launches of a GEMV kernel object into
+// `buf` ([slots][CTAs][8] u64, device memory); slots == 0 switches it off.
+extern "C" B200MM_API int b200mm_debug_gemv_trace(b200mm_kernel* k, void* buf, int slots) {
+    if (!k) return B200MM_ERR_INVALID;
+    k->trace_buf = slots > 0 ? (unsigned long long*)buf : nullptr;
+    k->trace_slots = slots;
+    k->trace_next = 0;
     return B200MM_OK;
 }
 

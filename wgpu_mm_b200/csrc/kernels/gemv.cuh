@@ -84,6 +84,16 @@ __device__ __forceinline__ void store_y(float* y, int gc, float v, const PeerSto
     }
 }
 
+// Debug timeline (tools/trace_gemv.py): when the upper bits of `use_cluster` carry a slot number, `tickets` is a trace buffer and
+// every CTA records globaltimer stamps at its milestones: [slot][cta][8] u64.  Zero cost when no slot is given (one predicate).
+__device__ __forceinline__ void gemv_trace(unsigned long long* t, int idx) {
+    if (t != nullptr && threadIdx.x == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        t[idx] = now;
+    }
+}
+
 // Launch: grid (panels, splits, batch), block WARPS*32.
 //   LPR   lanes per row segment (32 or 16): a warp reads 32/LPR rows per load instruction
 //   panel = LPR * COLS columns;   rows of a split are dealt round-robin to (warp, row-in-warp) slots.
@@ -133,6 +143,14 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     // Programmatic dependent launch: let the next kernel in the stream start as soon as SM resources free up, and do
     // not touch anything a previous kernel may still produce (x, partials, tickets, y) before griddepcontrol.wait.
     // The weights never depend on the previous kernel, so their first loads overlap its tail (no-ops without PDL).
+    unsigned long long* trace = nullptr;
+    if (use_cluster >> 8) {
+        const size_t ctas = (size_t)gridDim.x * gridDim.y * gridDim.z;
+        const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        trace = reinterpret_cast<unsigned long long*>(tickets) + ((size_t)((use_cluster >> 8) - 1) * ctas + cta) * 8;
+        use_cluster &= 0xff;
+    }
+    gemv_trace(trace, 0);  // CTA started
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     typename T::Vec wa[UNROLL], wb[UNROLL];
     auto issue = [&](typename T::Vec (&w)[UNROLL], int kk) {
@@ -145,6 +163,9 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     constexpr bool EAGER = EAGER_ < 0 ? (T::COLS == 4) : (EAGER_ != 0);
     issue(wa, k);
     if constexpr (EAGER) issue(wb, k + UNROLL * RSTEP);
+    // (Measured and rejected, round 2: prefetch.global.L2 of the CTA's whole weight slab at this point.  The median CTA finished
+    // streaming 1.5 us earlier, but the early-resident CTAs' prefetches competed with the draining launch and the slowest CTAs
+    // got slower: 12.9 -> 14.5 us at cfg4, profiles/r2_gemv_timeline.txt.)
     // grouped scales of this CTA's rows x columns -> shared memory (weights: independent of the previous kernel)
     float* ss = red + (WARPS * MROWS + MROWS) * PANEL;
     const int g0 = GROUPED ? k_beg / group_k : 0;
@@ -157,7 +178,9 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
             ss[i] = (g < groups && gc < N) ? __ldg(sc + (size_t)g * N + gc) : 0.f;
         }
     }
+    gemv_trace(trace, 1);  // first loads issued
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    gemv_trace(trace, 2);  // previous grid complete
     // N-sharded chain with deferred completion: x may derive from the y the peers stored during the PREVIOUS launch
     if (peers.world > 1 && peers.flags[0] != nullptr && peers.deferred && peers.epoch > 1) {
         peer_wait_epoch(peers, peers.epoch - 1);
@@ -174,6 +197,7 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
         for (int i = tid; i < n4; i += WARPS * 32) xs4[i] = i < valid4 ? __ldg(xg + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
+    gemv_trace(trace, 3);  // x staged
 
     float acc[MROWS][COLS];
 #pragma unroll
@@ -272,6 +296,7 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
         }
     }
 
+    gemv_trace(trace, 4);  // warp 0 finished streaming
     if constexpr (GROUPED) {
         fold(cur_g);
 #pragma unroll
@@ -315,6 +340,7 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
             for (int w = 0; w < WARPS; ++w) s += red[((w * MROWS + m) * COLS + cc % COLS) * LPR + cc / COLS];
             cta_part[c] = s;
         }
+        gemv_trace(trace, 5);  // CTA partial ready, entering the cluster barrier
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
         if (split == 0) {
             const uint32_t local = smem_u32(cta_part);
@@ -338,8 +364,10 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
                 if (gc < N) store_y(y + (size_t)m * N, gc, s * out_scale, peers);
             }
         }
+        gemv_trace(trace, 6);  // y stored (split 0) / waiting for the cluster leader
         // nobody may exit (and release its shared memory) before rank 0 has read every partial
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        gemv_trace(trace, 7);  // exit
         if (split == 0) peer_signal_and_wait(peers);
         return;
     }
