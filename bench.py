@@ -368,14 +368,14 @@ def run_single(args):
     npC = np.ctypeslib.as_array((C.c_float * (M * N)).from_address(hC.value))
     sets[0][0].read_into(npA); sets[0][1].read_into(npB)
     dA, dB, dC = sets[1]
-    e2e_steps = max(3, min(steps, 10))
-    for _ in range(2):
+    e2e_steps = 0 if args.no_e2e else max(3, min(steps, 10))
+    for _ in range(2 if e2e_steps else 0):
         ctx.mm_host(kern, npA, npB, npC, dA, dB, dC)
     te = time.perf_counter()
     for _ in range(e2e_steps):
         ctx.mm_host(kern, npA, npB, npC, dA, dB, dC)  # blocking: returns when C is in host memory
-    e2e_s = (time.perf_counter() - te) / e2e_steps
-    e2e = {"value": flop / e2e_s / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": M * K * 4 + K * N * 4, "d2h_bytes_per_step": M * N * 4,
+    e2e_s = (time.perf_counter() - te) / max(e2e_steps, 1)
+    e2e = None if args.no_e2e else {"value": flop / e2e_s / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": M * K * 4 + K * N * 4, "d2h_bytes_per_step": M * N * 4,
            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "api": "b200mm_mm_host (pinned host A,B -> device, split_lo + tcgen05 GEMM, C -> pinned host; copies pipelined over 16 row panels)"}
     checksum = float(npC[:4096].astype(np.float64).sum())
     for h in (hA, hB, hC):
@@ -642,7 +642,7 @@ def run_multi(args):
                 # kernel-only time of the per-rank panel (no peers, no cross-rank wait): the per-GPU roofline number
                 yl = ctx.buffer(gplan.cols * 4)
                 ksets = [(gj.x, Wb, yl) for Wb in gj.Ws]
-                kl = ctx.kernel(w.KernelId.QGEMV_SINT8 if quant else w.KernelId.GEMV_F32, 1, gplan.cols, Kv, w.KernelParams(absmax=2.0, batch=1))
+                kl = ctx.kernel(w.KernelId.QGEMV_SINT8 if quant else w.KernelId.GEMV_F32, 1, gplan.cols, Kv, w.KernelParams(absmax=2.0, batch=1, flags=int(w.Flags.AUTOTUNE)))
                 kms = time_back_to_back(ctx, kl, ksets, 200, 20)
                 kl.free(); yl.free()
                 tt = torch.tensor([gms / nstep, kms, grel], dtype=torch.float64, device="cuda")

@@ -45,7 +45,7 @@ def main():
             t = torch.tensor([best], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             yl = ctx.buffer(plan.cols * 4)
-            kl = ctx.kernel(w.KernelId.QGEMV_SINT8 if quant else w.KernelId.GEMV_F32, 1, plan.cols, K, w.KernelParams(absmax=2.0, batch=1))
+            kl = ctx.kernel(w.KernelId.QGEMV_SINT8 if quant else w.KernelId.GEMV_F32, 1, plan.cols, K, w.KernelParams(absmax=2.0, batch=1, flags=int(w.Flags.AUTOTUNE)))
             for _ in range(20):
                 ctx.launch(kl, gj.x, gj.Ws[0], yl)
             ctx.sync(); ctx.timer_begin()
@@ -54,7 +54,7 @@ def main():
             kms = ctx.timer_end() / 200
             kl.free(); yl.free()
             if rank == 0:
-                print(f"{'sint8' if quant else 'fp32 '} K={K} N={N} ({note}) x{world} {mode}{' deferred' if deferred else ''}: step {float(t) * 1e3:7.2f} us   panel-only kernel {kms * 1e3:6.2f} us", flush=True)
+                print(f"{'sint8' if quant else 'fp32 '} K={K} N={N} ({note}) x{world} {mode}{' deferred' if deferred else ''}: step {float(t) * 1e3:7.2f} us   panel-only kernel {kms * 1e3:6.2f} us  geometry {gj.kern.geometry()}", flush=True)
             gj.close()
     ctx.close()
     dist.destroy_process_group()

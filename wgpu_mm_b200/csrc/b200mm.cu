@@ -753,7 +753,7 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     int splits = (int)k->prm.tune[1];
     if (splits <= 0) {
         int occ = 1;
-        const size_t smem_guess = ((size_t)K / 4 + (size_t)warps * panel) * sizeof(float);
+        const size_t smem_guess = ((size_t)K / 4 + (size_t)(warps + 8) * panel) * sizeof(float);
         CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, warps * 32, smem_guess));
         occ = std::max(1, std::min(occ, 2048 / (warps * 32)));
@@ -780,7 +780,7 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     }
     const int rstep = group_k ? 128 : warps * (32 / lpr);  // grouped: splits start on a pipeline-window boundary
     auto smem_for = [&](size_t rows) {
-        size_t b = ((size_t)mrows * rows + (size_t)warps * mrows * panel + (size_t)mrows * panel) * sizeof(float);
+        size_t b = ((size_t)mrows * rows + (size_t)warps * mrows * panel + (size_t)8 * mrows * panel) * sizeof(float);  // x, warp partials, 8 cluster receive slots
         if (group_k) b += ((rows / group_k + 2) * panel + (size_t)warps * 32 * cols) * sizeof(float);  // scales + per-thread totals
         return b;
     };
@@ -854,11 +854,13 @@ static int gemv_autotune(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     cudaEvent_t e0, e1;
     CU_TRY(ctx, cudaEventCreate(&e0));
     CU_TRY(ctx, cudaEventCreate(&e1));
-    static const int f32_variants[] = {5, 100, 2, 3};
+    // small fp32 matrices (the per-rank panels of an N-sharded run: 32 MiB at 8 GPUs) are short of bytes in flight with the
+    // 128-column panels of the large-matrix geometries: the 64-column (16-lane) instantiations double the CTA count
+    static const int f32_variants[] = {5, 100, 2, 3, 1, 4, 6, 7};
     static const int s8_variants[] = {4, 11, 12, 13};
     static const int s8g_variants[] = {4, 11, 12, 14};
     const int* variants = quant ? (group_k ? s8g_variants : s8_variants) : f32_variants;
-    const int nvar = 4;
+    const int nvar = quant ? 4 : (wbytes <= ((size_t)96 << 20) ? 8 : 4);
     const uint64_t launches_before = ctx->launches;
     float best_ms = 1e30f, default_ms = 1e30f;
     uint32_t best_v = 0, best_s = 0;

@@ -167,7 +167,7 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     // streaming 1.5 us earlier, but the early-resident CTAs' prefetches competed with the draining launch and the slowest CTAs
     // got slower: 12.9 -> 14.5 us at cfg4, profiles/r2_gemv_timeline.txt.)
     // grouped scales of this CTA's rows x columns -> shared memory (weights: independent of the previous kernel)
-    float* ss = red + (WARPS * MROWS + MROWS) * PANEL;
+    float* ss = red + (WARPS * MROWS + 8 * MROWS) * PANEL;  // behind the 8 receive slots of the cluster reduction
     const int g0 = GROUPED ? k_beg / group_k : 0;
     const int ngl = GROUPED ? rows_per_split / group_k + 2 : 0;
     if constexpr (GROUPED) {
@@ -181,6 +181,9 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     gemv_trace(trace, 1);  // first loads issued
     asm volatile("griddepcontrol.wait;" ::: "memory");
     gemv_trace(trace, 2);  // previous grid complete
+    // split arrive / wait: tells the cluster this CTA is running (its shared memory may be written remotely from here on);
+    // the matching wait sits in front of the first remote store, ~10 us later
+    if (use_cluster && gridDim.y > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
     // N-sharded chain with deferred completion: x may derive from the y the peers stored during the PREVIOUS launch
     if (peers.world > 1 && peers.flags[0] != nullptr && peers.deferred && peers.epoch > 1) {
         peer_wait_epoch(peers, peers.epoch - 1);
@@ -328,45 +331,38 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     // warps -> CTA partial (fixed order), then K-splits (fixed order)
     const size_t pbase = ((size_t)batch * splits) * N;
     if (use_cluster && splits > 1) {
-        // The K-splits of one panel form a thread-block cluster (cluster dims (1, splits, 1)): every CTA leaves its partial
-        // in its own shared memory, rank 0 sums them in rank order through distributed shared memory and writes y.  This
-        // replaces partial store + __threadfence + atomic ticket + reload (three serialized global round trips, ~3 us)
-        // by two cluster barriers -- it matters because the whole sint8 kernel should take ~10 us.
-        float* cta_part = red + WARPS * MROWS * PANEL;  // MROWS * PANEL floats
+        // The K-splits of one panel form a thread-block cluster (cluster dims (1, splits, 1)).  Every CTA PUSHES its partial
+        // into slot `split` of the leader's (rank 0) shared memory through distributed shared memory, one cluster barrier makes
+        // the pushes visible, and the leader sums the slots in rank order from its OWN shared memory and writes y.  Round 1 let
+        // the leader pull the partials instead, which needed a second barrier to keep the peers' shared memory alive and put
+        // a DSMEM read latency on the leader's critical path (tools/trace_gemv.py: 1.6 us from "partial ready" to "exit" of a
+        // ~13 us launch).  This replaces partial store + __threadfence + atomic ticket + reload (three serialized global round
+        // trips, ~3 us) of the non-cluster path.
+        float* recv = red + WARPS * MROWS * PANEL;  // leader: [8 slots][MROWS * PANEL] floats
+        // the start-of-kernel arrive (below the PDL wait) pairs with this wait: every CTA of the cluster is known to be
+        // running before its shared memory is written remotely (already complete by now: no cost)
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        uint32_t leader;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(leader) : "r"(smem_u32(recv)), "r"(0));
+        leader += 4u * (uint32_t)(split * MROWS * PANEL);
         for (int c = tid; c < MROWS * PANEL; c += WARPS * 32) {
             const int m = c / PANEL, cc = c % PANEL;
             float s = 0.f;
 #pragma unroll
             for (int w = 0; w < WARPS; ++w) s += red[((w * MROWS + m) * COLS + cc % COLS) * LPR + cc / COLS];
-            cta_part[c] = s;
+            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(leader + 4u * c), "f"(s) : "memory");
         }
-        gemv_trace(trace, 5);  // CTA partial ready, entering the cluster barrier
+        gemv_trace(trace, 5);  // CTA partial pushed, entering the cluster barrier
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        gemv_trace(trace, 6);  // all partials of the panel have landed at the leader
         if (split == 0) {
-            const uint32_t local = smem_u32(cta_part);
             for (int c = tid; c < MROWS * PANEL; c += WARPS * 32) {
                 const int m = c / PANEL, gc = panel * PANEL + c % PANEL;
-                // all remote reads first (<= 8 splits in a cluster), then the fixed-order sum: one DSMEM latency instead of `splits`
-                float v[8];
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    v[r] = 0.f;
-                    if (r < splits) {
-                        uint32_t remote;
-                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local + 4u * c), "r"(r));
-                        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v[r]) : "r"(remote) : "memory");
-                    }
-                }
                 float s = 0.f;
-#pragma unroll
-                for (int r = 0; r < 8; ++r)
-                    if (r < splits) s += v[r];
+                for (int r = 0; r < splits; ++r) s += recv[r * MROWS * PANEL + c];  // fixed order: deterministic
                 if (gc < N) store_y(y + (size_t)m * N, gc, s * out_scale, peers);
             }
         }
-        gemv_trace(trace, 6);  // y stored (split 0) / waiting for the cluster leader
-        // nobody may exit (and release its shared memory) before rank 0 has read every partial
-        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
         gemv_trace(trace, 7);  // exit
         if (split == 0) peer_signal_and_wait(peers);
         return;

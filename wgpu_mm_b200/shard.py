@@ -236,7 +236,7 @@ class ShardedGemv:
     nccl: local slice + all_gather_into_tensor (slices are contiguous)."""
 
     def __init__(self, ctx, K: int, N: int, plan: ShardPlan, quant: bool = False, mode: str = "fused", seed: int = 300,
-                 x_host=None, panel_host=None, absmax: float = 2.0, nsets: int = 1, deferred: bool = True):
+                 x_host=None, panel_host=None, absmax: float = 2.0, nsets: int = 1, deferred: bool = True, autotune: bool = True):
         import torch
         import torch.distributed as dist
         import wgpu_mm_b200 as w
@@ -268,7 +268,8 @@ class ShardedGemv:
         self.y = ctx.buffer(2 * N * 4)  # two y buffers, alternated by step parity (fused mode)
         self.peers = []
         kid = w.KernelId.QGEMV_SINT8 if quant else w.KernelId.GEMV_F32
-        self.kern = ctx.kernel(kid, 1, Np, K, w.KernelParams(absmax=absmax, batch=1))
+        # the per-rank panel is a small matrix: let the library measure the launch geometry once (B200MM_F_AUTOTUNE)
+        self.kern = ctx.kernel(kid, 1, Np, K, w.KernelParams(absmax=absmax, batch=1, flags=int(w.Flags.AUTOTUNE) if autotune else 0))
         if mode == "fused":
             self.flags = ctx.buffer(64)
             self.flags.write(np.zeros(16, dtype=np.uint32))
