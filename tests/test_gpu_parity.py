@@ -113,6 +113,44 @@ def test_sgemm_tc3x(gpu_ctx, oracle, shape, bn):
     _check(oracle, got, A, B)
 
 
+@pytest.mark.parametrize("shape", [(256, 256, 256), (512, 768, 1024), (300, 520, 260), (1024, 1024, 1024), (130, 260, 36), (2304, 2048, 768), (257, 1001, 515)])
+def test_sgemm_tc3x_cta_pairs(gpu_ctx, oracle, shape):
+    """The 2-CTA instantiation (tune[0] = 512: 256 x 256 tiles on CTA pairs, tcgen05 cta_group::2), forced on shapes the default
+    rule would give to single CTAs: ragged edges (a pair whose second CTA is entirely out of range), stream-K tails, and the
+    padded path.  Same gates as the 1-CTA kernel, and bit-identical to it where the K-split schedule coincides."""
+    import wgpu_mm_b200 as w
+    M, N, K = shape
+    A = oracle.generate_weight_data(19, M, K)
+    B = oracle.generate_weight_data(20, K, N)
+    got = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K, w.KernelParams(tune=(512, 0, 0, 0)))
+    assert not (got == 123.25).any()
+    _check(oracle, got, A, B)
+    again = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K, w.KernelParams(tune=(512, 0, 0, 0)))
+    assert np.array_equal(got, again)
+    if K <= 256:  # one chain per tile: no K-split anywhere, so the two kernels perform the same arithmetic
+        single = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K, w.KernelParams(tune=(513, 0, 0, 0)))
+        assert np.array_equal(got, single)
+
+
+def test_sgemm_tc3x_cta_pairs_at_the_baseline_shape(gpu_ctx, oracle):
+    """4096^3 takes the pair kernel by default (512 pair tiles >= 74 SM pairs): sampled rows vs FP64 / mm_ref, checksum of all tiles."""
+    import wgpu_mm_b200 as w
+    M = N = K = 4096
+    A = oracle.generate_weight_data(21, M, K)
+    B = oracle.generate_weight_data(22, K, N)
+    kern = gpu_ctx.kernel(w.KernelId.SGEMM_TC3X, M, N, K)
+    grid, block = kern.geometry()
+    assert grid[0] == 148 and block[0] == 384
+    kern.free()
+    got = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K)
+    rows = np.array(sorted({0, 127, 128, 255, 256, 2051, 4095}))
+    e, m = oracle.err_vs_f64(got[rows], oracle.mm_f64_rows(A, B, rows))
+    assert e / m <= REL_F64
+    assert oracle.max_abs_err(got[rows], oracle.mm_ref(A[rows], B)) <= GATE
+    cs = A.astype(np.float64).sum(axis=0) @ B.astype(np.float64)
+    assert np.abs(got.astype(np.float64).sum(axis=0) - cs).max() <= 1e-6 * M * np.abs(cs).max() + 1e-3
+
+
 @pytest.mark.parametrize("shape", [(100, 36, 20), (129, 260, 36), (500, 1000, 252), (128, 4, 4), (128, 130, 66), (48, 4096, 4096), (1, 7, 5),
                                    (100, 37, 21), (257, 1001, 515), (300, 64, 1027), (13, 14336, 4096)])
 def test_sgemm_tc3x_ragged(gpu_ctx, oracle, shape):

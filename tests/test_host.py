@@ -193,7 +193,7 @@ TC3X_SHAPES = [(4096, 4096, 4096), (16384, 2048, 16384), (128, 4096, 4096), (256
 
 
 @pytest.mark.parametrize("shape", TC3X_SHAPES)
-@pytest.mark.parametrize("cfg", [(256, 16), (256, 32), (128, 32)])
+@pytest.mark.parametrize("cfg", [(256, 16), (256, 32), (128, 32), (512, 16)])  # bn = 512: the 2-CTA kernel (256 x 256 tiles on SM pairs)
 @pytest.mark.parametrize("pure", [0, 1])
 def test_tc3x_schedule_covers_every_unit_once(shape, cfg, pure):
     """The SGEMM_TC3X work schedule (hybrid waves + stream-K, or the uniform k-split when tiles < SMs) as the kernel's own
@@ -205,8 +205,13 @@ def test_tc3x_schedule_covers_every_unit_once(shape, cfg, pure):
     out = (C.c_int * 6)()
     assert lib().b200mm_tc3x_schedule(M, N, K, bn, bk, sms, pure, out) == 0
     grid, full_waves, cpt, k_split, tiles, sk_units = list(out)
-    assert tiles == -(-M // 128) * -(-N // bn) and cpt == -(-(-(-K // bk)) // (256 // bk))
-    assert 1 <= grid <= sms
+    if bn == 512:  # grid counts CTA pairs
+        assert tiles == -(-M // 256) * -(-N // 256) and cpt == -(-(-(-K // bk)) // (256 // bk))
+        units = sms // 2
+    else:
+        assert tiles == -(-M // 128) * -(-N // bn) and cpt == -(-(-(-K // bk)) // (256 // bk))
+        units = sms
+    assert 1 <= grid <= units
     cover = np.zeros(tiles * cpt, dtype=np.uint16)
     mseg, mch = C.c_int(), C.c_int()
     assert lib().b200mm_tc3x_schedule_cover(M, N, K, bn, bk, sms, pure, cover.ctypes.data_as(C.c_void_p), cover.size, C.byref(mseg), C.byref(mch)) == 0
@@ -216,9 +221,9 @@ def test_tc3x_schedule_covers_every_unit_once(shape, cfg, pure):
     assert mch.value <= full_waves * cpt + -(-sk_units // grid)
     if k_split and not pure:
         # fewer tiles than SMs: one segment per CTA, every tile cut into the same k_split slices
-        assert tiles < sms and cpt % k_split == 0 and grid == tiles * k_split and tiles * k_split <= sms
+        assert tiles < units and cpt % k_split == 0 and grid == tiles * k_split and tiles * k_split <= units
         assert mseg.value == 1 and mch.value == cpt // k_split
-        assert all(cpt % d or tiles * d > sms for d in range(k_split + 1, cpt + 1))  # k_split is the largest admissible divisor
+        assert all(cpt % d or tiles * d > units for d in range(k_split + 1, cpt + 1))  # k_split is the largest admissible divisor
 
 
 # shapes where stream-K units < CTAs, so some CTAs have an empty range (the advisor's hang list) + the regular ones
@@ -227,7 +232,7 @@ TC3X_REPLAY_SHAPES = TC3X_SHAPES + [(4096, 4096, 512), (16384, 16384, 512), (409
 
 
 @pytest.mark.parametrize("shape", TC3X_REPLAY_SHAPES)
-@pytest.mark.parametrize("cfg", [(256, 16), (256, 32), (128, 32)])
+@pytest.mark.parametrize("cfg", [(256, 16), (256, 32), (128, 32), (512, 16)])
 @pytest.mark.parametrize("pure", [0, 1])
 def test_tc3x_stream_k_fixup_protocol_replay(shape, cfg, pure):
     """Replays the owner/contributor dependency graph of the stream-K tail with the kernel's own contributor rule: a finisher

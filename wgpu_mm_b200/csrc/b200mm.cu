@@ -65,6 +65,7 @@ struct b200mm_kernel {
     float* b_hi = nullptr;                   // padded copy of B, only when N % 32 != 0
     CUtensorMap tmAh{}, tmAl{}, tmBh{}, tmBl{};
     int tc_bn = 256, tc_bk = 32;
+    bool tc_cta2 = false;  // 2-CTA (cta_group::2) instantiation: 256 x 256 tiles on CTA pairs
     const void *tc_a_src = nullptr, *tc_b_src = nullptr;  // operands the hi tensor maps currently point at
     bool tc_b_copy = false;                               // ragged N: B is staged into a padded copy first
     float4* tc_partial = nullptr;
@@ -427,6 +428,7 @@ extern "C" const char* b200mm_kernel_name(int id) {
 
 using Tc256 = Tc3xCfg<256, 2, false, 32>;     // 2 stages x 96 KB
 using Tc256k16 = Tc3xCfg<256, 4, false, 16>;  // 4 stages x 48 KB: same bytes in flight, finer refill granularity
+using Tc256k16x2 = Tc3xCfg<256, 6, false, 16, 256, true>;  // 2-CTA pairs: 256 x 256 tiles, 6 stages x 32 KB per CTA
 using Tc128 = Tc3xCfg<128, 3, false, 32>;
 using Tc256x1 = Tc3xCfg<256, 4, true, 32>;
 
@@ -632,6 +634,15 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     k->tc_bk = (k->prm.tune[2] == 32) ? 32 : 16;  // default: BK = 16, 4 stages
     if (one_pass) k->tc_bn = 256;
     if (one_pass || k->tc_bn == 128) k->tc_bk = 32;
+    // tune[0] = 512: the 2-CTA kernel (256 x 256 tiles on CTA pairs, cta_group::2); 513: force the 1-CTA kernel.  Default: pairs when
+    // there are at least as many 256-row tiles as SM pairs (big GEMMs), single CTAs otherwise (skinny M: a pair would idle one SM).
+    {
+        const long long tiles2 = (long long)ceil_div(M, 256) * (long long)ceil_div(N, 256);
+        const bool want2 = k->prm.tune[0] == 512 || (k->prm.tune[0] == 0 && tiles2 >= ctx->prop.multiProcessorCount / 2 && getenv("B200MM_TC3X_1CTA") == nullptr);
+        k->tc_cta2 = want2 && !one_pass && k->tc_bn == 256 && ctx->prop.multiProcessorCount % 2 == 0;
+        if (k->tc_cta2) k->tc_bk = 16;
+    }
+    const int tile_m = k->tc_cta2 ? 256 : 128;
     // workspace: lo parts of both operands (the raw operands are consumed as hi); for N % 32 != 0 also a padded
     // copy of B, because the 3-D view (n%32, k, n/32) of a ragged N reads up to 124 B past the last row
     const size_t a_bytes = M * K * sizeof(float), b_bytes = K * N * sizeof(float) + 128;
@@ -640,8 +651,9 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     // schedule (see Tc3xArgs / tc3x_make_schedule): units = tiles x chains, one contiguous range per CTA
     const int bk = k->tc_bk;
     const int sms = ctx->prop.multiProcessorCount;
-    const Tc3xSchedule sched = tc3x_make_schedule(M, N, K, k->tc_bn, bk, sms, k->prm.tune[1] == 1);  // tune[1] = 1: pure stream-K (experiments)
-    const int grid_x = sched.grid;
+    // scheduling units: SMs, or SM pairs for the 2-CTA kernel
+    const Tc3xSchedule sched = tc3x_make_schedule(M, N, K, k->tc_bn, bk, k->tc_cta2 ? sms / 2 : sms, k->prm.tune[1] == 1, tile_m);  // tune[1] = 1: pure stream-K (experiments)
+    const int grid_x = sched.grid * (k->tc_cta2 ? 2 : 1);
     k->tc_cpt = sched.chains_per_tile;
     k->tc_full_waves = sched.full_waves;
     k->tc_sk_units = sched.sk_units;
@@ -650,8 +662,8 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     // does the rest while earlier bands are multiplied.  tune[3] = 1 keeps the whole split in the pre-pass (round-1 behaviour).
     k->tc_bands = (int)ceil_div(M, (size_t)kTc3xBandRows);
     {
-        const long long band_tiles = (long long)kTc3xGroupM * (long long)ceil_div(N, (size_t)k->tc_bn);
-        const long long first_wave = std::min<long long>(grid_x, sched.tiles);
+        const long long band_tiles = (long long)(kTc3xBandRows / tile_m) * (long long)ceil_div(N, (size_t)k->tc_bn);
+        const long long first_wave = std::min<long long>(sched.grid, sched.tiles);
         long long pre = sched.full_waves == 0 ? k->tc_bands : (first_wave + band_tiles - 1) / band_tiles;
         if (k->prm.tune[3] == 1 || one_pass) pre = k->tc_bands;
         k->tc_prebands = (int)std::min<long long>(std::max<long long>(pre, 1), k->tc_bands);
@@ -678,12 +690,15 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     int rc;
     if (!one_pass) {
         if ((rc = make_tmap_kmajor(ctx, &k->tmAl, k->a_lo, M, K, 128, bk))) return rc;
-        if ((rc = make_tmap_mnmajor(ctx, &k->tmBl, k->b_lo, K, N, bk, k->tc_bn))) return rc;
+        if ((rc = make_tmap_mnmajor(ctx, &k->tmBl, k->b_lo, K, N, bk, k->tc_cta2 ? k->tc_bn / 2 : k->tc_bn))) return rc;
     }
     // the hi maps point at the caller's A and B and are (re)encoded at launch time
     k->grid = dim3(grid_x, 1, 1);
     k->block = dim3(Tc256::THREADS, 1, 1);
-    if (one_pass) {
+    if (k->tc_cta2) {
+        k->smem = Tc256k16x2::SMEM_BYTES;
+        CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc256k16x2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
+    } else if (one_pass) {
         k->smem = Tc256x1::SMEM_BYTES;
         CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc256x1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
     } else if (k->tc_bn == 256 && k->tc_bk == 16) {
@@ -1096,7 +1111,7 @@ static cudaError_t launch_tc3x(b200mm_kernel* k, cudaStream_t s, const float* A,
     a.N = (int)k->N;
     a.K = (int)k->K;
     a.ldc = (int)k->N;
-    a.tiles_m = (int)ceil_div(k->M, Cfg::BM);
+    a.tiles_m = (int)ceil_div(k->M, Cfg::TILE_M);
     a.tiles_n = (int)ceil_div(k->N, Cfg::BN);
     a.chains_per_tile = k->tc_cpt;
     a.full_waves = k->tc_full_waves;
@@ -1113,11 +1128,18 @@ static cudaError_t launch_tc3x(b200mm_kernel* k, cudaStream_t s, const float* A,
     cfg.blockDim = k->block;
     cfg.dynamicSmemBytes = k->smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = (k->tc_prebands < k->tc_bands) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if constexpr (Cfg::CTA2) {  // CTA pairs: a cluster of two CTAs is placed on one TPC
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = 2;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+    }
     return cudaLaunchKernelEx(&cfg, sgemm_tc3x_kernel<Cfg>, k->tmAh, k->tmAl, k->tmBh, k->tmBl, a);
 }
 
@@ -1213,7 +1235,7 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
                 k->tc_a_src = A;
             }
             if (k->tc_b_src != b_src) {
-                if ((rc = make_tmap_mnmajor(ctx, &k->tmBh, (const float*)b_src, k->K, k->N, k->tc_bk, k->tc_bn))) return rc;
+                if ((rc = make_tmap_mnmajor(ctx, &k->tmBh, (const float*)b_src, k->K, k->N, k->tc_bk, k->tc_cta2 ? k->tc_bn / 2 : k->tc_bn))) return rc;
                 k->tc_b_src = b_src;
             }
             cudaError_t le;
@@ -1234,7 +1256,9 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
                                                         skip_b ? 0 : b4);
                 ctx->launches += 1;
                 prof_begin();
-                if (k->tc_bn == 256 && k->tc_bk == 16)
+                if (k->tc_cta2)
+                    le = launch_tc3x<Tc256k16x2>(k, s, Af, Cf);
+                else if (k->tc_bn == 256 && k->tc_bk == 16)
                     le = launch_tc3x<Tc256k16>(k, s, Af, Cf);
                 else if (k->tc_bn == 256)
                     le = launch_tc3x<Tc256>(k, s, Af, Cf);
@@ -1506,9 +1530,13 @@ extern "C" int b200mm_unshard_columns(b200mm_ctx* ctx, const void* gathered, voi
 // debug: tcgen05 bring-up probe (tools/probe_tc.py); not part of the public header
 // ------------------------------------------------------------------------------------------------
 // ---- device-free introspection of the tc3x schedule (tests/test_host.py) ---------------------------------------------------
+// bn == 512 selects the schedule of the 2-CTA kernel: 256 x 256 tiles over sms / 2 CTA pairs (out[0] = number of pairs)
+static Tc3xSchedule tc3x_sched_for(size_t M, size_t N, size_t K, int bn, int bk, int sms, bool pure) {
+    return bn == 512 ? tc3x_make_schedule(M, N, K, 256, bk, sms / 2, pure, 256) : tc3x_make_schedule(M, N, K, bn, bk, sms, pure);
+}
 extern "C" int b200mm_tc3x_schedule(size_t M, size_t N, size_t K, int bn, int bk, int sms, int pure_stream_k, int out[6]) {
-    if (!out || !M || !N || !K || (bn != 128 && bn != 256) || (bk != 16 && bk != 32) || sms <= 0) return B200MM_ERR_INVALID;
-    const Tc3xSchedule sc = tc3x_make_schedule(M, N, K, bn, bk, sms, pure_stream_k != 0);
+    if (!out || !M || !N || !K || (bn != 128 && bn != 256 && bn != 512) || (bk != 16 && bk != 32) || sms <= 0) return B200MM_ERR_INVALID;
+    const Tc3xSchedule sc = tc3x_sched_for(M, N, K, bn, bk, sms, pure_stream_k != 0);
     out[0] = sc.grid;
     out[1] = sc.full_waves;
     out[2] = sc.chains_per_tile;
@@ -1520,8 +1548,8 @@ extern "C" int b200mm_tc3x_schedule(size_t M, size_t N, size_t K, int bn, int bk
 
 extern "C" int b200mm_tc3x_schedule_cover(size_t M, size_t N, size_t K, int bn, int bk, int sms, int pure_stream_k, uint16_t* cover,
                                           size_t cover_len, int* max_segments_per_cta, int* max_chains_per_cta) {
-    if (!cover || !M || !N || !K || (bn != 128 && bn != 256) || (bk != 16 && bk != 32) || sms <= 0) return B200MM_ERR_INVALID;
-    const Tc3xSchedule sc = tc3x_make_schedule(M, N, K, bn, bk, sms, pure_stream_k != 0);
+    if (!cover || !M || !N || !K || (bn != 128 && bn != 256 && bn != 512) || (bk != 16 && bk != 32) || sms <= 0) return B200MM_ERR_INVALID;
+    const Tc3xSchedule sc = tc3x_sched_for(M, N, K, bn, bk, sms, pure_stream_k != 0);
     if (cover_len < (size_t)sc.tiles * sc.chains_per_tile) return B200MM_ERR_INVALID;
     int max_seg = 0, max_ch = 0;
     for (int b = 0; b < sc.grid; ++b) {
@@ -1546,8 +1574,8 @@ extern "C" int b200mm_tc3x_schedule_cover(size_t M, size_t N, size_t K, int bn, 
 // exactly.  Returns B200MM_OK and *violations == 0 when the protocol is consistent (no wait on a CTA that never publishes).
 extern "C" int b200mm_tc3x_schedule_replay(size_t M, size_t N, size_t K, int bn, int bk, int sms, int pure_stream_k, int* violations,
                                            int* max_wait_list) {
-    if (!violations || !M || !N || !K || (bn != 128 && bn != 256) || (bk != 16 && bk != 32) || sms <= 0) return B200MM_ERR_INVALID;
-    const Tc3xSchedule sc = tc3x_make_schedule(M, N, K, bn, bk, sms, pure_stream_k != 0);
+    if (!violations || !M || !N || !K || (bn != 128 && bn != 256 && bn != 512) || (bk != 16 && bk != 32) || sms <= 0) return B200MM_ERR_INVALID;
+    const Tc3xSchedule sc = tc3x_sched_for(M, N, K, bn, bk, sms, pure_stream_k != 0);
     struct Parked { int tile, c0, c1; };
     std::vector<Parked> parked(sc.grid, Parked{-1, 0, 0});
     std::vector<int> publishes(sc.grid, 0);

@@ -120,6 +120,55 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
         : "memory");
 }
 
+// cta_group::2 forms (CTA pair on one TPC): the TMA lands in the issuing CTA's shared memory but signals the mbarrier of the
+// pair's leader (bit 24 of a shared::cluster address is the CTA rank inside the pair; clearing it addresses the leader).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both CTAs: 128 rows each] * B[smem of both CTAs: N/2 columns each]; issued by the leader only
+__device__ __forceinline__ void mma_tf32_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t z = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(z)
+        : "memory");
+}
+// arrives on the mbarrier at the same shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {  // arrive on the leader's copy of a barrier from the peer CTA
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(0));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
 }
@@ -242,9 +291,8 @@ struct SegIter {  // identical iteration in the producer, issuer and epilogue ro
         u = (long long)block * sk_units / grid;
         u1 = (long long)(block + 1) * sk_units / grid;
     }
-#ifdef __CUDACC__
-    __device__ SegIter(const Tc3xArgs& p) : SegIter(p.chains_per_tile, p.full_waves, p.sk_units, (int)blockIdx.x, (int)gridDim.x) {}
-#endif
+    // unit = CTA (1-CTA tiles) or CTA pair (2-CTA tiles): both CTAs of a pair walk the same schedule
+    __host__ __device__ SegIter(const Tc3xArgs& p, int unit, int units) : SegIter(p.chains_per_tile, p.full_waves, p.sk_units, unit, units) {}
     // c1 != cpt => contributor segment (parked); c1 == cpt && c0 != 0 => finisher of a split tile; sk_tile = tile index inside phase 2
     __host__ __device__ bool next(int& tile, int& c0, int& c1, int& sk_tile) {
         if (wave < full_waves) {
@@ -292,11 +340,13 @@ struct Tc3xSchedule {
     int chains_per_tile, full_waves, grid, k_split;  // k_split > 0: uniform split of every tile (tiles < SMs)
     long long tiles, sk_units;
 };
-inline Tc3xSchedule tc3x_make_schedule(size_t M, size_t N, size_t K, int bn, int bk, int sms, bool pure_stream_k) {
+// `sms` = number of schedulable units: SMs for 128-row tiles, SM PAIRS for the 256-row tiles of the 2-CTA kernel (tile_m = 256);
+// sc.grid counts units.
+inline Tc3xSchedule tc3x_make_schedule(size_t M, size_t N, size_t K, int bn, int bk, int sms, bool pure_stream_k, int tile_m = 128) {
     Tc3xSchedule sc{};
     const size_t chain = 256 / bk, num_kb = (K + bk - 1) / bk;
     sc.chains_per_tile = (int)((num_kb + chain - 1) / chain);
-    sc.tiles = (long long)((M + 127) / 128) * (long long)((N + bn - 1) / bn);
+    sc.tiles = (long long)((M + tile_m - 1) / tile_m) * (long long)((N + bn - 1) / bn);
     // hybrid schedule: whole-tile waves while there is >= one tile per SM, stream-K over the remainder
     long long grid = sc.tiles * sc.chains_per_tile < sms ? sc.tiles * sc.chains_per_tile : sms;
     if (sc.tiles < sms && !pure_stream_k) {
@@ -321,9 +371,17 @@ inline Tc3xSchedule tc3x_make_schedule(size_t M, size_t N, size_t K, int bn, int
 // Measured on B200 (tools/debug_tc3x.py): the tensor core adds into its fp32 accumulator with truncation, so a
 // single chain over K = 4096 (1536 accumulate steps) is biased by ~1e-4 -- 10x worse than a sequential fp32 loop.
 // Chains of 8 k-blocks (256 k, 96 steps) folded with round-to-nearest FADDs bring the error back to the fp32 level.
-template <int BN_, int STAGES_, bool ONE_PASS_, int BK_ = 32, int CHAIN_K_ = 256>
+// CTA2: the tile is 256 x BN and belongs to a PAIR of CTAs on one TPC (cluster of 2, tcgen05 cta_group::2): each CTA stages its
+// own 128 rows of A and HALF of the B tile, the leader issues one MMA for both tensor cores, each CTA drains its own
+// 128 x BN accumulator.  Per SM and k-step that is 2 x (A 128 x BK + B BK x BN/2) instead of 2 x (A + B BK x BN): a third less
+// L2 -> shared-memory traffic and a third less operand reads per MMA -- energy, on a kernel that runs into the power cap.
+template <int BN_, int STAGES_, bool ONE_PASS_, int BK_ = 32, int CHAIN_K_ = 256, bool CTA2_ = false>
 struct Tc3xCfg {
     static constexpr int BM = 128, BN = BN_, BK = BK_, STAGES = STAGES_, CHAIN = CHAIN_K_ / BK_;
+    static constexpr bool CTA2 = CTA2_;
+    static constexpr int TILE_M = CTA2 ? 256 : 128;   // rows of C per scheduled tile
+    static constexpr int BN_CTA = CTA2 ? BN / 2 : BN;  // columns of the B tile staged by one CTA
+    static_assert(!CTA2 || !ONE_PASS_, "the 2-CTA kernel is the 3xTF32 one");
     static_assert(BK == 32 || BK == 16, "A tile rows are 128 B (SWIZZLE_128B) or 64 B (SWIZZLE_64B)");
     static constexpr uint32_t A_LAYOUT = BK == 32 ? kLayoutSw128 : kLayoutSw64;
     static constexpr uint32_t A_SBO = 8 * BK * 4;               // 8 rows of BK floats
@@ -332,7 +390,7 @@ struct Tc3xCfg {
     static constexpr int THREADS = 128 + EPI_WARPS * 32;       // warps 0-3: TMA / MMA / TMEM alloc / idle
     static constexpr int COLS_PER_WG = BN / 2;
     static constexpr uint32_t A_BYTES = BM * BK * 4;           // 128 rows x BK floats, K-major
-    static constexpr uint32_t B_BYTES = BK * BN * 4;           // BN/32 atoms x (BK k-rows x 128 B), SWIZZLE_128B_BASE32B, MN-major
+    static constexpr uint32_t B_BYTES = BK * BN_CTA * 4;       // BN_CTA/32 atoms x (BK k-rows x 128 B), SWIZZLE_128B_BASE32B, MN-major
     static constexpr uint32_t STAGE_BYTES = (ONE_PASS ? 1 : 2) * (A_BYTES + B_BYTES);
     static constexpr uint32_t TMEM_COLS = 2 * BN;              // two chain accumulators (ping-pong)
     static constexpr uint32_t EPI_STAGE_LD = 32;                                   // floats per staged row; 16 B chunks XOR-swizzled by row
@@ -349,8 +407,15 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                   const __grid_constant__ Tc3xArgs p) {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, CHAIN = Cfg::CHAIN;
-    constexpr bool ONE_PASS = Cfg::ONE_PASS;
+    constexpr bool ONE_PASS = Cfg::ONE_PASS, CTA2 = Cfg::CTA2;
+    constexpr int TILE_M = Cfg::TILE_M, BN_CTA = Cfg::BN_CTA;
+    constexpr int GROUP_M = kTc3xBandRows / TILE_M;  // tile rows per rasterisation band (= per split band of A)
     constexpr uint32_t A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
+    // scheduling unit: this CTA, or the CTA pair it belongs to (2-CTA tiles); cta_rank = position inside the pair
+    uint32_t cta_rank = 0;
+    if constexpr (CTA2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    const int unit = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int units = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms are 1024 B aligned
@@ -385,17 +450,25 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(tfull_bar(s), 1);
-            ptx::mbar_init(tempty_bar(s), Cfg::EPI_WARPS);  // one arrive per epilogue warp
+            ptx::mbar_init(tempty_bar(s), (CTA2 ? 2 : 1) * Cfg::EPI_WARPS);  // one arrive per epilogue warp (of both CTAs of a pair)
         }
         ptx::fence_barrier_init();
         for (int i = 0; i < Cfg::EPI_WARPS; ++i) tiles_done_ptr()[i] = 0;
     }
     if (warp == 2) {
-        ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-        ptx::tmem_relinquish();
+        if constexpr (CTA2) {
+            ptx::tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);  // one warp of EACH CTA of the pair, same slot offset
+            ptx::tmem_relinquish_pair();
+        } else {
+            ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (CTA2)
+        ptx::cluster_sync_all();  // the peer's barriers are initialised and its TMEM allocated before anything is signalled remotely
+    else
+        __syncthreads();
     ptx::tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -405,7 +478,6 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     // m-fastest order streams ALL of A through L2 every wave once tiles_m >= 128: measured 193 vs 265 TFLOP/s
     // for 16384^3 vs 4096^3 on one GPU.)
     auto tile_coords = [&](int t, int& tm, int& tn) {
-        constexpr int GROUP_M = kTc3xGroupM;
         const int band_tiles = GROUP_M * p.tiles_n;
         const int band = t / band_tiles;
         const int first_m = band * GROUP_M;
@@ -421,14 +493,14 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             if (lane == 0) {
                 int stage = 0;
                 uint32_t phase = 0;
-                SegIter it(p);
+                SegIter it(p, unit, units);
                 int t, c0, c1, skt;
                 int ready_band = p.prebands - 1;  // bands are completed in order: one high-water mark suffices
                 while (it.next(t, c0, c1, skt)) {
                     int tm, tn;
                     tile_coords(t, tm, tn);
                     if (!ONE_PASS) {
-                        const int band = tm / kTc3xGroupM;
+                        const int band = tm / GROUP_M;
                         if (band > ready_band) {
                             // A_lo of this band is being produced by the splitter warps of ALL CTAs of this launch
                             const unsigned int target = p.epoch * gridDim.x;
@@ -443,12 +515,23 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
                     const int kb_end = min(c1 * CHAIN, num_kb);
                     for (int kb = c0 * CHAIN; kb < kb_end; ++kb) {
                         ptx::mbar_wait(empty_bar(stage), phase ^ 1);
-                        ptx::mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-                        ptx::tma_load_2d(sA_hi(stage), &tmAh, full_bar(stage), kb * BK, tm * BM);
-                        ptx::tma_load_3d(sB_hi(stage), &tmBh, full_bar(stage), 0, kb * BK, tn * (BN / 32));
-                        if (!ONE_PASS) {
-                            ptx::tma_load_2d(sA_lo(stage), &tmAl, full_bar(stage), kb * BK, tm * BM);
-                            ptx::tma_load_3d(sB_lo(stage), &tmBl, full_bar(stage), 0, kb * BK, tn * (BN / 32));
+                        if constexpr (CTA2) {
+                            // both CTAs load their own 128 rows of A and their half of the B tile into their OWN shared memory;
+                            // all transaction bytes are counted on the leader's barrier, which the leader's MMA issuer waits on
+                            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+                            const int arow = tm * TILE_M + (int)cta_rank * BM, bcol = tn * (BN / 32) + (int)cta_rank * (BN_CTA / 32);
+                            ptx::tma_load_2d_pair(sA_hi(stage), &tmAh, full_bar(stage), kb * BK, arow);
+                            ptx::tma_load_3d_pair(sB_hi(stage), &tmBh, full_bar(stage), 0, kb * BK, bcol);
+                            ptx::tma_load_2d_pair(sA_lo(stage), &tmAl, full_bar(stage), kb * BK, arow);
+                            ptx::tma_load_3d_pair(sB_lo(stage), &tmBl, full_bar(stage), 0, kb * BK, bcol);
+                        } else {
+                            ptx::mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+                            ptx::tma_load_2d(sA_hi(stage), &tmAh, full_bar(stage), kb * BK, tm * BM);
+                            ptx::tma_load_3d(sB_hi(stage), &tmBh, full_bar(stage), 0, kb * BK, tn * (BN / 32));
+                            if (!ONE_PASS) {
+                                ptx::tma_load_2d(sA_lo(stage), &tmAl, full_bar(stage), kb * BK, tm * BM);
+                                ptx::tma_load_3d(sB_lo(stage), &tmBl, full_bar(stage), 0, kb * BK, tn * (BN / 32));
+                            }
                         }
                         if (++stage == STAGES) {
                             stage = 0;
@@ -459,12 +542,12 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             }
         } else if (warp == 1) {
             // ===================== MMA issuer =====================
-            if (lane == 0) {
-                constexpr uint32_t idesc = make_idesc_tf32(BM, BN, /*A MN-major*/ false, /*B MN-major*/ true);
+            if (lane == 0 && cta_rank == 0) {  // 2-CTA tiles: the leader issues for both tensor cores
+                constexpr uint32_t idesc = make_idesc_tf32(TILE_M, BN, /*A MN-major*/ false, /*B MN-major*/ true);
                 int stage = 0;
                 uint32_t phase = 0;
                 uint32_t chain = 0;  // running chain index: TMEM buffer = chain & 1
-                SegIter it(p);
+                SegIter it(p, unit, units);
                 int t, c0, c1, skt;
                 while (it.next(t, c0, c1, skt)) {
                     for (int kb0 = c0 * CHAIN; kb0 < min(c1 * CHAIN, num_kb); kb0 += CHAIN, ++chain) {
@@ -484,7 +567,14 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
                                 // LBO = stride between 32-column atoms = BK rows x 128 B
                                 const uint64_t b_hi = make_smem_desc(sB_hi(stage) + j * 1024, BK * 128, 512, kLayoutSw128Base32B);
                                 const uint32_t acc0 = (kb > kb0 || j > 0) ? 1u : 0u;  // first MMA of a chain overwrites
-                                if (!ONE_PASS) {
+                                if constexpr (CTA2) {
+                                    // descriptors name the leader's shared memory; the peer's operands sit at the same offsets
+                                    const uint64_t a_lo = make_smem_desc(sA_lo(stage) + j * 32, 16, Cfg::A_SBO, Cfg::A_LAYOUT);
+                                    const uint64_t b_lo = make_smem_desc(sB_lo(stage) + j * 1024, BK * 128, 512, kLayoutSw128Base32B);
+                                    ptx::mma_tf32_ss_pair(d_tmem, a_lo, b_hi, idesc, acc0);  // small terms first
+                                    ptx::mma_tf32_ss_pair(d_tmem, a_hi, b_lo, idesc, 1u);
+                                    ptx::mma_tf32_ss_pair(d_tmem, a_hi, b_hi, idesc, 1u);
+                                } else if (!ONE_PASS) {
                                     const uint64_t a_lo = make_smem_desc(sA_lo(stage) + j * 32, 16, Cfg::A_SBO, Cfg::A_LAYOUT);
                                     const uint64_t b_lo = make_smem_desc(sB_lo(stage) + j * 1024, BK * 128, 512, kLayoutSw128Base32B);
                                     ptx::mma_tf32_ss(d_tmem, a_lo, b_hi, idesc, acc0);  // small terms first
@@ -494,13 +584,15 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
                                     ptx::mma_tf32_ss(d_tmem, a_hi, b_hi, idesc, acc0);
                                 }
                             }
-                            ptx::mma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
+                            // smem stage reusable once these MMAs retire (2-CTA: in both CTAs)
+                            if constexpr (CTA2) ptx::mma_commit_pair(empty_bar(stage)); else ptx::mma_commit(empty_bar(stage));
                             if (++stage == STAGES) {
                                 stage = 0;
                                 phase ^= 1;
                             }
                         }
-                        ptx::mma_commit(tfull_bar(as));  // chain complete -> epilogue
+                        // chain complete -> epilogue (of both CTAs)
+                        if constexpr (CTA2) ptx::mma_commit_pair(tfull_bar(as)); else ptx::mma_commit(tfull_bar(as));
                     }
                 }
             }
@@ -540,7 +632,7 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             // streams the tile (L2-hot) to the same position of C on every peer over NVLink.  The NVLink back-pressure
             // therefore never reaches the warps that drain TMEM, and the MMA pipeline keeps running (measured at 8 GPUs:
             // stores issued by the epilogue warps themselves cost 16 % of the kernel).
-            SegIter it(p);
+            SegIter it(p, unit, units);
             int t, c0, c1, skt;
             unsigned int stored = 0;
             const float* src_base = p.peers.c[p.peers.rank];
@@ -554,9 +646,10 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
                 __threadfence();
                 int tm, tn;
                 tile_coords(t, tm, tn);
-                const int rows = min(BM, p.M - tm * BM);
+                const int trow0 = tm * TILE_M + (int)cta_rank * BM;  // this CTA's 128 rows of the tile
+                const int rows = max(0, min(BM, p.M - trow0));
                 const int cols4 = min(BN, p.N - tn * BN) / 4;  // float4 per tile row
-                const size_t off0 = (size_t)(tm * BM) * p.peers.ldc + p.peers.col0 + (size_t)tn * BN;
+                const size_t off0 = (size_t)trow0 * p.peers.ldc + p.peers.col0 + (size_t)tn * BN;
                 for (int r = 0; r < rows; r += 8) {
                     // 8 rows x up to 64 float4 per row are read ONCE (16 independent 16-byte loads in flight per lane) and
                     // fanned out from registers to every peer
@@ -593,7 +686,7 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         const int half = (warp - 4) >> 2;
         uint32_t chain = 0;
         const int etid = threadIdx.x - 128;  // 0..255 inside the epilogue group
-        SegIter it(p);
+        SegIter it(p, unit, units);
         int t, c0, c1, skt;
         while (it.next(t, c0, c1, skt)) {
             int tm, tn;
@@ -616,7 +709,12 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+                if (lane == 0) {
+                    if (CTA2 && cta_rank != 0)
+                        ptx::mbar_arrive_leader(tempty_bar(as));  // the leader's issuer waits for the epilogues of both CTAs
+                    else
+                        ptx::mbar_arrive(tempty_bar(as));
+                }
             }
             if (c1 != p.chains_per_tile) {
                 // contributor: this range ends inside the tile -> park the partial sums for the finisher (a higher-numbered CTA)
@@ -631,14 +729,15 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             if (c0 != 0) {
                 // finisher of a tile that began in preceding CTAs: add their parts in CTA order.  Only lower-numbered,
                 // non-empty CTAs are waited on (see Tc3xArgs).
-                const int j0 = tc3x_first_contributor(skt, p.chains_per_tile, p.sk_units, (int)blockIdx.x, (int)gridDim.x);
-                for (int j = j0; j < (int)blockIdx.x; ++j) {
-                    if (tc3x_cta_is_empty(j, p.sk_units, (int)gridDim.x)) continue;
+                const int j0 = tc3x_first_contributor(skt, p.chains_per_tile, p.sk_units, unit, units);
+                for (int j = j0; j < unit; ++j) {
+                    if (tc3x_cta_is_empty(j, p.sk_units, units)) continue;
+                    const int jc = CTA2 ? 2 * j + (int)cta_rank : j;  // the CTA of unit j that holds the same 128 rows
                     unsigned int seen;
                     do {
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.flags + j) : "memory");
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.flags + jc) : "memory");
                     } while (seen != p.epoch);
-                    const float4* slot = p.partial + (size_t)j * (COLS / 4) * 256;
+                    const float4* slot = p.partial + (size_t)jc * (COLS / 4) * 256;
 #pragma unroll
                     for (int jj = 0; jj < COLS / 4; ++jj) {
                         const float4 w = __ldcg(slot + jj * 256 + etid);
@@ -654,7 +753,7 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             // 4 KB of shared memory (XOR-swizzled, conflict-free) so that each st.global.v4 covers 4 rows x 128 contiguous bytes -- full 128 B lines for
             // HBM and for NVLink when the tile also goes to the peers (fused all-gather).
             float* stage = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw))) + (warp - 4) * 32 * Cfg::EPI_STAGE_LD;
-            const int row0 = tm * BM + q * 32;
+            const int row0 = tm * TILE_M + (int)cta_rank * BM + q * 32;
             const int col0 = tn * BN + half * COLS;
             float* const base = p.peers.world == 0 ? p.C : p.peers.c[p.peers.rank];  // fused mode: local copy only, see replicator
             const size_t ld = p.peers.world == 0 ? (size_t)p.ldc : p.peers.ldc;
@@ -688,10 +787,13 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (CTA2)
+        ptx::cluster_sync_all();  // neither CTA may free TMEM / exit while the pair's MMAs or remote arrives are in flight
+    else
+        __syncthreads();
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if constexpr (CTA2) ptx::tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); else ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
