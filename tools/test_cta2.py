@@ -15,9 +15,9 @@ for (M, N, K) in shapes:
     a = ctx.buffer(M * K * 4); a.fill_weights(1, M * K)
     b = ctx.buffer(K * N * 4); b.fill_weights(2, K * N)
     outs, times = [], []
-    for tune0 in (513, 512):
+    for tune0, bk in ((513, 0), (512, 0)) + (((512, 32),) if os.environ.get("BK32") else ()):
         c = ctx.buffer_from(np.full(M * N, 7.0, dtype=np.float32))
-        k = ctx.kernel(w.KernelId.SGEMM_TC3X, M, N, K, w.KernelParams(tune=(tune0, 0, 0, 0)))
+        k = ctx.kernel(w.KernelId.SGEMM_TC3X, M, N, K, w.KernelParams(tune=(tune0, 0, bk, 0)))
         ctx.launch(k, a, b, c)
         outs.append(c.read(np.float32).reshape(M, N))
         for _ in range(3):
@@ -26,7 +26,7 @@ for (M, N, K) in shapes:
         for _ in range(5):
             ctx.launch(k, a, b, c)
         times.append(ctx.timer_end() / 5)
-        print(f"   tune {tune0}: geometry {k.geometry()}", flush=True)
+        print(f"   tune {tune0} bk {bk}: geometry {k.geometry()}  {times[-1] * 1e3:.1f} us", flush=True)
         k.free(); c.free()
     A = a.read(np.float32).reshape(M, K).astype(np.float64)
     B = b.read(np.float32).reshape(K, N).astype(np.float64)

@@ -429,6 +429,7 @@ extern "C" const char* b200mm_kernel_name(int id) {
 using Tc256 = Tc3xCfg<256, 2, false, 32>;     // 2 stages x 96 KB
 using Tc256k16 = Tc3xCfg<256, 4, false, 16>;  // 4 stages x 48 KB: same bytes in flight, finer refill granularity
 using Tc256k16x2 = Tc3xCfg<256, 6, false, 16, 256, true>;  // 2-CTA pairs: 256 x 256 tiles, 6 stages x 32 KB per CTA
+using Tc256k32x2 = Tc3xCfg<256, 3, false, 32, 256, true>;  // same with BK = 32: 3 stages x 64 KB (tune[2] = 32; measured, not the default)
 using Tc128 = Tc3xCfg<128, 3, false, 32>;
 using Tc256x1 = Tc3xCfg<256, 4, true, 32>;
 
@@ -640,7 +641,7 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
         const long long tiles2 = (long long)ceil_div(M, 256) * (long long)ceil_div(N, 256);
         const bool want2 = k->prm.tune[0] == 512 || (k->prm.tune[0] == 0 && tiles2 >= ctx->prop.multiProcessorCount / 2 && getenv("B200MM_TC3X_1CTA") == nullptr);
         k->tc_cta2 = want2 && !one_pass && k->tc_bn == 256 && ctx->prop.multiProcessorCount % 2 == 0;
-        if (k->tc_cta2) k->tc_bk = 16;
+        if (k->tc_cta2) k->tc_bk = (k->prm.tune[2] == 32) ? 32 : 16;
     }
     const int tile_m = k->tc_cta2 ? 256 : 128;
     // workspace: lo parts of both operands (the raw operands are consumed as hi); for N % 32 != 0 also a padded
@@ -695,7 +696,10 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     // the hi maps point at the caller's A and B and are (re)encoded at launch time
     k->grid = dim3(grid_x, 1, 1);
     k->block = dim3(Tc256::THREADS, 1, 1);
-    if (k->tc_cta2) {
+    if (k->tc_cta2 && k->tc_bk == 32) {
+        k->smem = Tc256k32x2::SMEM_BYTES;
+        CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc256k32x2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
+    } else if (k->tc_cta2) {
         k->smem = Tc256k16x2::SMEM_BYTES;
         CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc256k16x2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
     } else if (one_pass) {
@@ -1256,7 +1260,9 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
                                                         skip_b ? 0 : b4);
                 ctx->launches += 1;
                 prof_begin();
-                if (k->tc_cta2)
+                if (k->tc_cta2 && k->tc_bk == 32)
+                    le = launch_tc3x<Tc256k32x2>(k, s, Af, Cf);
+                else if (k->tc_cta2)
                     le = launch_tc3x<Tc256k16x2>(k, s, Af, Cf);
                 else if (k->tc_bn == 256 && k->tc_bk == 16)
                     le = launch_tc3x<Tc256k16>(k, s, Af, Cf);
