@@ -324,6 +324,7 @@ def run_single(args):
     # ---------------- headline: tcgen05 3xTF32 SGEMM 4096^3 ----------------
     tune = (args.tc_bn, 0, args.tc_bk, 0)
     kern = ctx.kernel(w.KernelId.SGEMM_TC3X, M, N, K, w.KernelParams(tune=tune))
+    tc_grid_pairs = args.tc_bn in (0, 512)  # 4096^3: 256 pair tiles >= 74 SM pairs, so the default rule picks the pair kernel
     sets = make_sets(ctx, M, N, K, 3, 100)
     sampler = ClockSampler(0); sampler.start(); time.sleep(0.3)
     t0 = sampler.mark()
@@ -346,15 +347,18 @@ def run_single(args):
         except Exception as exc:  # noqa: BLE001
             measured = {"error": repr(exc)}
     derived_peak = peaks["bf16_tflops"] / 2.0 / 3.0
-    tc_peak = measured["tf32_tflops"] / 3.0 if "tf32_tflops" in measured else derived_peak
+    measured_peak = measured["tf32_tflops"] / 3.0 if "tf32_tflops" in measured else None
+    # Conservative denominator: the LARGER of the two TF32 ceilings -- cuBLAS TF32 measured in this run, and half the measured
+    # bf16 burst rate of MEASURED_PEAKS.json (cuBLAS' TF32 kernels do not reach half of its bf16 rate on this part, so the
+    # measured figure alone would flatter the kernel).  Both are reported.
+    tc_peak = max(measured_peak or 0.0, derived_peak)
     traffic = load_traffic()
     roofline = {"bound": "tensor", "achieved": tc_achieved, "peak": tc_peak, "unit": "TFLOP/s", "frac": tc_achieved / tc_peak,
                 "traffic": traffic.get("sgemm_tc3x_kernel@4096"), "traffic_source": traffic.get("_source"),
                 "kernel": "sgemm_tc3x_kernel", "kernel_ms": kern_ms,
                 "per_step_frac": value / tc_peak,
-                "peak_source": ("cuBLAS TF32 8192^3 burst measured in this run (extras.measured_peaks.tf32_tflops) / 3 (3xTF32 MMAs per product)"
-                                if "tf32_tflops" in measured else
-                                f"DERIVED: MEASURED_PEAKS.json bf16_tflops ({peaks['_source']}, burst) / 2 / 3 -- the in-run TF32 measurement failed"),
+                "peak_source": "max(cuBLAS TF32 8192^3 burst measured in this run, MEASURED_PEAKS.json bf16_tflops burst / 2) / 3 (3xTF32 MMAs per product)",
+                "peak_measured_cublas_tf32_div_3": measured_peak, "frac_of_measured_cublas_tf32": (tc_achieved / measured_peak if measured_peak else None),
                 "peak_derived_bf16_div_6": derived_peak, "frac_of_derived": tc_achieved / derived_peak,
                 "tensor_pipe_view": f"{3 * tc_achieved:.1f} TF32 TFLOP/s executed"}
 
@@ -497,7 +501,7 @@ def run_single(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3 (fp32-accurate, fp32 accumulate)",
         "data": "synthetic U[-10,10)/50, seeded, generated on device",
         "config": {"workload": f"sgemm {M}x{N}x{K} fp32 row-major", "baseline_config": "BASELINE configs[1]", "kernel": "sgemm_tc3x (split_lo + tcgen05 GEMM per step)",
-                   "tile": f"128x{args.tc_bn}x{args.tc_bk or 16}", "l2": "3 rotating (A,B,C) sets = 576 MiB of operands, larger than the 126 MB L2",
+                   "tile": ("256x256x16 on CTA pairs (cta_group::2)" if tc_grid_pairs else f"128x{args.tc_bn or 256}x{args.tc_bk or 16}"), "l2": "3 rotating (A,B,C) sets = 576 MiB of operands, larger than the 126 MB L2",
                    "device": info["name"], "sm_count": info["sm_count"]},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "extras": extras, "c_checksum": checksum,
@@ -702,7 +706,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="fused", choices=["fused", "nccl"], help="multi-GPU gather: peer stores from the epilogue, or NCCL all-gather")
     ap.add_argument("--size", type=int, default=16384, help="multi-GPU problem size (M=N=K)")
-    ap.add_argument("--tc-bn", type=int, default=256, choices=[128, 256])
+    ap.add_argument("--tc-bn", type=int, default=0, choices=[0, 128, 256, 512, 513],
+                    help="sgemm_tc3x tune[0]: 0 = library default (2-CTA pair kernel for big GEMMs), 512 / 513 = force the 2-CTA / 1-CTA kernel, 128 / 256 = 1-CTA with that BN")
     ap.add_argument("--tc-bk", type=int, default=0, choices=[0, 16, 32], help="k-block of the tcgen05 kernel (0 = library default)")
     ap.add_argument("--gemv-variant", type=int, default=0)
     ap.add_argument("--no-extras", action="store_true")

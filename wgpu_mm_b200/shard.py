@@ -83,7 +83,7 @@ class PeerBarrier:
 class ShardedSgemm:
     """One 16384^3-style job on this rank.  Requires torch.distributed (NCCL) to be initialised."""
 
-    def __init__(self, ctx, M: int, N: int, K: int, plan: ShardPlan, mode: str = "fused", kernel_id=None, seed: int = 100, tc_bn: int = 256):
+    def __init__(self, ctx, M: int, N: int, K: int, plan: ShardPlan, mode: str = "fused", kernel_id=None, seed: int = 100, tc_bn: int = 0):
         import torch
         import torch.distributed as dist
         import wgpu_mm_b200 as w
