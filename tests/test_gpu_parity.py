@@ -322,6 +322,37 @@ def test_qgemv_sint8(gpu_ctx, oracle, kn, variant):
     assert oracle.max_abs_err(got, oracle.wgsl_qgemv_1(x, words, N, K, 2.0)) <= 1e-4
 
 
+@pytest.mark.parametrize("case", [("s8", 4096, 14336, 21, 2, 148), ("s8", 4096, 14336, 21, 1, 296), ("s8", 1024, 1024, 21, 2, 40), ("s8", 1000, 1040, 13, 2, 9),
+                                  ("s8", 512, 4096, 21, 4, 74), ("f32", 1024, 2048, 5, 2, 20), ("f32", 4096, 16384, 5, 4, 148), ("f32", 300, 260, 4, 1, 7)])
+def test_gemv_balanced_ragged_panels(gpu_ctx, oracle, case):
+    """tune[3] = explicit panel count: the column groups are dealt evenly to that many (ragged) panels so that a grid can be sized
+    to exactly one CTA slot per panel x split.  Same results as the natural partition, bit for bit per column (the row order of
+    each column's sum does not depend on which panel owns it) as long as the K-split is the same."""
+    import wgpu_mm_b200 as w
+    kind, K, N, variant, splits, panels = case
+    x = oracle.generate_weight_data(27, 1, K)
+    W = oracle.generate_weight_data(28, K, N)
+    if kind == "s8":
+        words, _ = oracle.sint8_quantize(W, K, N)
+        kid, B, dt = w.KernelId.QGEMV_SINT8, words, np.uint32
+        want, f64 = oracle.qgemv_ref(x, words, 1, N, K, 2.0), oracle.qgemv_f64(x, words, 1, N, K, 2.0)
+    else:
+        kid, B, dt = w.KernelId.GEMV_F32, W, np.float32
+        want, f64 = oracle.mm_ref(x, W), oracle.mm_f64(x, W)
+    got = _run(gpu_ctx, kid, x, B, 1, N, K, w.KernelParams(absmax=2.0, batch=1, tune=(variant, splits, 0, panels)), b_dtype=dt)
+    assert not (got == 123.25).any()
+    assert oracle.max_abs_err(got, want) <= GATE
+    e, m = oracle.err_vs_f64(got, f64)
+    assert e / m <= REL_F64
+    kern = gpu_ctx.kernel(kid, 1, N, K, w.KernelParams(absmax=2.0, batch=1, tune=(variant, splits, 0, panels)))
+    assert kern.geometry()[0][0] == panels
+    kern.free()
+    natural = _run(gpu_ctx, kid, x, B, 1, N, K, w.KernelParams(absmax=2.0, batch=1, tune=(variant, splits, 0, 0)), b_dtype=dt)
+    assert np.array_equal(got, natural)
+    with pytest.raises(w.B200mmError):  # more column groups per panel than the instantiation is wide
+        gpu_ctx.kernel(kid, 1, N, K, w.KernelParams(absmax=2.0, batch=1, tune=(variant, splits, 0, 16)))
+
+
 def test_qgemv_true_absmax_and_extremes(gpu_ctx, oracle):
     """Sanity variant with the real absmax, and weights at +-127 (the int8 extremes the codec can emit)."""
     import wgpu_mm_b200 as w

@@ -469,6 +469,7 @@ static GemvPick gemv_pick(int variant, int mrows = 1, bool grouped = false) {
         if (variant == 11) return GEMV_INST(8, 4, 16, 1, false, 3);
         if (variant == 12) return GEMV_INST(8, 4, 16, 1, false, 4);
         if (variant == 13) return GEMV_INST(8, 4, 16, 1, false, 1, 1);
+        if (variant == 21) return GEMV_INST(8, 4, 8, 1, false, 1, 1);  // 128-column panels: the balanced (ragged-panel) grids, tune[3] = panel count
     } else {
         // skinny GEMM: only the default geometry of each weight type is instantiated for M = 2, 4, 8
         if (mrows == 2) return GEMV_INST(4, 4, 32, 2);
@@ -766,6 +767,14 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     const int panel = lpr * cols;
     const unsigned batch = k->prm.batch ? k->prm.batch : 1;
     k->panels = (int)ceil_div(N, panel);
+    if (k->prm.tune[3] >= 16) {
+        // explicit panel count: the column groups are dealt evenly to that many panels (balanced grids, gemv.cuh) -- e.g. one
+        // panel x split per CTA slot so that every SM carries the same load.  Each panel must fit the instantiation's width.
+        const size_t groups = N / cols, want = k->prm.tune[3];
+        if (want > groups || ceil_div(groups, want) > (size_t)lpr)
+            return fail(ctx, B200MM_ERR_INVALID, "%s: %zu panels do not fit %zu column groups at %d groups per panel", b200mm_kernel_name(k->id), want, groups, lpr);
+        k->panels = (int)want;
+    }
     // K-splits: fill exactly ONE wave.  A second, partial wave runs at a fraction of the bandwidth (few CTAs, few
     // loads in flight) and was measured to cost 25 % at cfg3, so the split count is rounded DOWN to what is
     // co-resident: SMs x occupancy of this instantiation (registers, x staging + reduction smem).
@@ -789,7 +798,7 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
         splits = (int)std::min<size_t>(splits, std::max<size_t>(1, K / 32));
     }
     // K-splits of a panel are reduced inside a thread-block cluster (<= 8 CTAs, portable size) unless tune[3] == 1
-    k->gemv_cluster = (k->prm.tune[3] != 1) || mrows > 1;  // the ticket path exists for M == 1 only
+    k->gemv_cluster = (k->prm.tune[3] != 1) || mrows > 1;  // the ticket path exists for M == 1 only; tune[3] >= 16 is a panel count
     if (mrows > 1 && splits > 8) splits = 8;
     if (k->gemv_cluster && splits > 8) {
         if (k->prm.tune[1] > 0)
@@ -931,6 +940,50 @@ static int gemv_autotune(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
             cudaStreamSynchronize(ctx->stream);
             if (t.ws) cudaFree(t.ws);
         }
+    // balanced grids (sint8, global scale): SMs x 2 CTA slots dealt as (panels x splits) with ragged 128-column panels
+    uint32_t best_p = 0;
+    if (quant && !group_k && rc == B200MM_OK) {
+        const uint32_t slots = (uint32_t)ctx->prop.multiProcessorCount * 2;
+        for (uint32_t sp : {1u, 2u, 4u}) {
+            const uint32_t panels = slots / sp;
+            if (panels < 16 || panels > N / 16 || ceil_div(N / 16, panels) > 8 || sp > K / 32) continue;
+            b200mm_kernel t;
+            t.id = k->id;
+            t.M = 1;
+            t.N = N;
+            t.K = K;
+            t.prm = k->prm;
+            t.prm.flags &= ~(B200MM_F_AUTOTUNE | B200MM_F_PEER_STORE);
+            t.prm.tune[0] = 21;
+            t.prm.tune[1] = sp;
+            t.prm.tune[3] = panels;
+            if (setup_gemv(ctx, &t, quant) != B200MM_OK || (uint32_t)t.splits != sp) {
+                if (t.ws) cudaFree(t.ws);
+                continue;
+            }
+            float ms = 1e30f;
+            for (int round = 0; round < 4 && rc == B200MM_OK; ++round) {
+                if (round) cudaEventRecord(e0, ctx->stream);
+                for (int i = 0; i < 64 && rc == B200MM_OK; ++i) rc = b200mm_launch_ptr(ctx, &t, x, W + (size_t)(i % nsets) * wbytes, y, nullptr);
+                if (round) {
+                    cudaEventRecord(e1, ctx->stream);
+                    if (cudaEventSynchronize(e1) != cudaSuccess) rc = fail(ctx, B200MM_ERR_CUDA, "gemv autotune: %s", cudaGetErrorString(cudaGetLastError()));
+                    float m = 0.f;
+                    cudaEventElapsedTime(&m, e0, e1);
+                    ms = std::min(ms, m / 64);
+                }
+            }
+            if (dbg) fprintf(stderr, "[b200mm] autotune %zux%zu balanced: variant 21, %u panels x %u splits: %.2f us\n", K, N, panels, sp, ms * 1e3f);
+            if (rc == B200MM_OK && ms < best_ms) {
+                best_ms = ms;
+                best_v = 21;
+                best_s = sp;
+                best_p = panels;
+            }
+            cudaStreamSynchronize(ctx->stream);
+            if (t.ws) cudaFree(t.ws);
+        }
+    }
     cudaStreamSynchronize(ctx->stream);
     ctx->launches = launches_before;
     cudaEventDestroy(e0);
@@ -944,9 +997,11 @@ static int gemv_autotune(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
         best_v = default_v;
         best_s = default_s;
         best_ms = default_ms;
+        best_p = 0;
     }
     k->prm.tune[0] = best_v;
     k->prm.tune[1] = best_s;
+    if (best_p) k->prm.tune[3] = best_p;
     if (dbg) fprintf(stderr, "[b200mm] autotune %zux%zu -> variant %u, %u splits, %.2f us\n", K, N, best_v, best_s, best_ms * 1e3f);
     return B200MM_OK;
 }

@@ -124,8 +124,17 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lir = lane % LPR, riw = lane / LPR;
     const int panel = blockIdx.x, split = blockIdx.y, batch = blockIdx.z, splits = gridDim.y;
-    const int col = panel * PANEL + lir * COLS;
-    const bool col_ok = col < N;  // N % COLS == 0 is required (N % 4 == 0 in the reference)
+    // Balanced column panels: the N / COLS column groups (one 128-bit load each) are dealt to the gridDim.x panels as evenly as
+    // possible, panel p = groups [p*G/P, (p+1)*G/P).  With the natural panel count ceil(G / LPR) this is the plain LPR-group
+    // partition; with MORE panels (the host's choice, e.g. exactly one CTA slot per panel x split so that every SM carries the same
+    // load) the panels are ragged and a few lanes of each row segment idle.  N % COLS == 0 is required (N % 4 == 0 in the
+    // reference); the host guarantees ceil(G / P) <= LPR.
+    const int n_groups = N / COLS;
+    const int grp0 = (int)((long long)panel * n_groups / (int)gridDim.x);
+    const int pcol0 = grp0 * COLS;                                                                  // first column of this panel
+    const int pcols = ((int)((long long)(panel + 1) * n_groups / (int)gridDim.x) - grp0) * COLS;    // its width (<= PANEL)
+    const int col = pcol0 + lir * COLS;
+    const bool col_ok = lir * COLS < pcols;
 
     x += batch * x_batch_stride;
     y += batch * y_batch_stride;
@@ -174,8 +183,8 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
         const float* sc = reinterpret_cast<const float*>(Wb + (size_t)K * N);
         const int groups = (K + group_k - 1) / group_k;
         for (int i = tid; i < ngl * PANEL; i += WARPS * 32) {
-            const int g = g0 + i / PANEL, gc = panel * PANEL + i % PANEL;
-            ss[i] = (g < groups && gc < N) ? __ldg(sc + (size_t)g * N + gc) : 0.f;
+            const int g = g0 + i / PANEL, gc = pcol0 + i % PANEL;
+            ss[i] = (g < groups && i % PANEL < pcols) ? __ldg(sc + (size_t)g * N + gc) : 0.f;
         }
     }
     gemv_trace(trace, 1);  // first loads issued
@@ -357,10 +366,10 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
         gemv_trace(trace, 6);  // all partials of the panel have landed at the leader
         if (split == 0) {
             for (int c = tid; c < MROWS * PANEL; c += WARPS * 32) {
-                const int m = c / PANEL, gc = panel * PANEL + c % PANEL;
+                const int m = c / PANEL, gc = pcol0 + c % PANEL;
                 float s = 0.f;
                 for (int r = 0; r < splits; ++r) s += recv[r * MROWS * PANEL + c];  // fixed order: deterministic
-                if (gc < N) store_y(y + (size_t)m * N, gc, s * out_scale, peers);
+                if (c % PANEL < pcols) store_y(y + (size_t)m * N, gc, s * out_scale, peers);
             }
         }
         gemv_trace(trace, 7);  // exit
@@ -369,8 +378,8 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     }
     for (int c = tid; c < MROWS * PANEL; c += WARPS * 32) {
         const int m = c / PANEL, cc = c % PANEL;
-        const int gc = panel * PANEL + cc;
-        if (gc >= N) continue;
+        const int gc = pcol0 + cc;
+        if (cc >= pcols) continue;
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) s += red[((w * MROWS + m) * COLS + cc % COLS) * LPR + cc / COLS];
@@ -391,8 +400,8 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     if (s_ticket != (unsigned)splits - 1) return;
     __threadfence();
     for (int c = tid; c < PANEL; c += WARPS * 32) {
-        const int gc = panel * PANEL + c;
-        if (gc >= N) continue;
+        const int gc = pcol0 + c;
+        if (c >= pcols) continue;
         // fixed summation order, but the L2 loads are issued 8 at a time (a one-at-a-time loop costs splits x ~0.4 us)
         float s = 0.f;
         for (int sp0 = 0; sp0 < splits; sp0 += 8) {
