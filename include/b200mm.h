@@ -82,7 +82,7 @@ typedef struct b200mm_kernel_params {
     uint32_t batch;             /* qgemv: number of (x, W, y) problems along global_id.y (qgemv_1.wgsl:12-14) */
     uint32_t flags;             /* B200MM_F_* below                                                            */
     uint32_t tune[4];           /* kernel-specific tuning knobs; 0 = default                                  */
-    uint32_t group_k;           /* qgemv_sint8 only: rows per quantisation group, a multiple of 128; 0 = the reference's one
+    uint32_t group_k;           /* qgemv_sint8 only: rows per quantisation group: 32, 64 or a multiple of 128; 0 = the reference's one
                                  * global absmax (src/quant.rs:17).  When > 0, B holds the K*N int8 weights followed by
                                  * ceil(K/group_k)*N f32 scales (per group and column) and `absmax` is ignored: SURVEY 8f rank 3. */
 } b200mm_kernel_params;

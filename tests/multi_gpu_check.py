@@ -77,6 +77,25 @@ def main():
             print(f"rank {rank}/{world} gemv mode={mode} quant={quant}: rel_f64={e / m:.3e} max_abs={mae:.3e} {'OK' if ok else 'FAIL'}", flush=True)
             failures += 0 if ok else 1
             job.close()
+    # ---- N-sharded sint8 GEMV with per-group scales (group_k = 128): every rank's panel carries its own columns' scales ----
+    from wgpu_mm_b200.quant import sint8_quantize_grouped, split_grouped
+    G = 128
+    plan = shard.ShardPlan(Nv, world, rank)
+    packed = sint8_quantize_grouped(Wf, Kv, Nv, G)
+    gwords, gscales = split_grouped(packed, Kv, Nv, G)
+    f64 = oracle.qgemv_grouped_f64(x, gwords, gscales, 1, Nv, Kv, G)
+    wpanel = np.ascontiguousarray(gwords.reshape(Kv, Nv // 4)[:, plan.col0 // 4:(plan.col0 + plan.cols) // 4])
+    spanel = np.ascontiguousarray(gscales.reshape(-1, Nv)[:, plan.col0:plan.col0 + plan.cols])
+    panel = np.concatenate([wpanel.reshape(-1).view(np.uint32), spanel.reshape(-1).view(np.uint32)])
+    job = shard.ShardedGemv(ctx, Kv, Nv, plan, quant=True, mode="fused", x_host=x, panel_host=panel, group_k=G)
+    for _ in range(3):
+        job.step()
+    got = job.result().reshape(1, Nv)
+    e, m = oracle.err_vs_f64(got, f64)
+    ok = e / m <= 5e-6
+    print(f"rank {rank}/{world} gemv mode=fused quant=grouped({G}): rel_f64={e / m:.3e} {'OK' if ok else 'FAIL'}", flush=True)
+    failures += 0 if ok else 1
+    job.close()
     t = torch.tensor([failures], device="cuda")
     dist.all_reduce(t)
     ctx.close()

@@ -412,7 +412,9 @@ def test_qgemv_1_port_batch_guard(gpu_ctx, oracle):
 
 
 GROUPED = [(1024, 1024, 128), (4096, 14336, 128), (4096, 14336, 256), (1000, 1040, 128), (64, 64, 128), (2048, 512, 2048),
-           (1536, 256, 512), (4096, 4096, 4096)]
+           (1536, 256, 512), (4096, 4096, 4096),
+           # GGUF-style small groups (round 2): a narrower pipeline window (UNROLL 2 / 1) so that it never straddles a group
+           (1024, 1024, 64), (1024, 1024, 32), (4096, 14336, 64), (4096, 14336, 32), (1000, 1040, 32), (96, 48, 64), (40, 16, 32)]
 
 
 @pytest.mark.parametrize("kng", GROUPED)
@@ -471,9 +473,15 @@ def test_qgemv_grouped_batched_and_errors(gpu_ctx, oracle):
         e, m = oracle.err_vs_f64(got[b:b + 1], oracle.qgemv_grouped_f64(x[b:b + 1], words, scales, 1, N, K, G))
         assert e / m <= REL_F64
     with pytest.raises(w.B200mmError):
-        gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 1, N, K, w.KernelParams(group_k=96))  # not a multiple of 128
+        gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 1, N, K, w.KernelParams(group_k=96))  # not 32, 64 or a multiple of 128
     with pytest.raises(w.B200mmError):
-        gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 2, N, K, w.KernelParams(group_k=128))  # M > 1
+        gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 2, N, K, w.KernelParams(group_k=128, batch=2))  # batched needs M == 1
+    # M > 1 with per-group scales: one pass per row of x (the grouped kernel is single-row)
+    X3 = oracle.generate_weight_data(66, 3, K)
+    got3 = _run(gpu_ctx, w.KernelId.QGEMV_SINT8, X3, packs[0], 3, N, K, w.KernelParams(batch=1, group_k=G), b_dtype=np.uint32)
+    words0, scales0 = split_grouped(packs[0], K, N, G)
+    e3, m3 = oracle.err_vs_f64(got3, oracle.qgemv_grouped_f64(X3, words0, scales0, 3, N, K, G))
+    assert e3 / m3 <= REL_F64
     with pytest.raises(w.B200mmError):
         gpu_ctx.kernel(w.KernelId.GEMV_F32, 1, N, K, w.KernelParams(group_k=128))  # fp32 weights carry no scales
     kern = gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 1, N, K, w.KernelParams(group_k=G))

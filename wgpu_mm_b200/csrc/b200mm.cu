@@ -453,9 +453,12 @@ struct GemvPick {
 #define GEMV_INST(W, U, L, ...) \
     GemvPick { gemv_stream_kernel<T, W, U, L, ##__VA_ARGS__>, W, L }
 
+// grouped: 0 = no per-group scales, else the quantisation group size (rows).  Groups of 64 / 32 rows need a pipeline window
+// (2 x UNROLL x 16 rows) that never straddles a group: UNROLL 2 / 1 instead of 4.
 template <class T>
-static GemvPick gemv_pick(int variant, int mrows = 1, bool grouped = false) {
+static GemvPick gemv_pick(int variant, int mrows = 1, size_t grouped = 0) {
     if constexpr (T::COLS == 16) {
+        if (grouped && grouped < 128) return grouped >= 64 ? GEMV_INST(8, 2, 16, 1, true, 2, 1) : GEMV_INST(8, 1, 16, 1, true, 2, 1);
         if (grouped) {
             switch (variant) {
                 case 11: return GEMV_INST(8, 4, 16, 1, true, 3);
@@ -724,15 +727,15 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     const int cols = quant ? 16 : 4;
     if (M > 16)
         return fail(ctx, B200MM_ERR_INVALID, "%s takes M <= 16 rows of x (skinny GEMM); use an SGEMM kernel for larger M", b200mm_kernel_name(k->id));
-    if (M != 1 && M != 2 && M != 4 && !(M == 8 && !quant)) {
+    if ((M != 1 && M != 2 && M != 4 && !(M == 8 && !quant)) || (M > 1 && k->prm.group_k)) {
         // no instantiation for this row count: chunks of 8 / 4 / 2 / 1 rows, each one pass over W (a second pass over a
         // sint8 matrix of the BASELINE size is served from L2)
         if (k->prm.batch > 1) return fail(ctx, B200MM_ERR_INVALID, "%s: batch > 1 needs M in {1, 2, 4%s}", b200mm_kernel_name(k->id), quant ? "" : ", 8");
-        if (k->prm.group_k) return fail(ctx, B200MM_ERR_INVALID, "qgemv_sint8 with group_k: M must be 1");
         if (k->prm.flags & B200MM_F_PEER_STORE) return fail(ctx, B200MM_ERR_INVALID, "%s: peer stores need M == 1", b200mm_kernel_name(k->id));
         size_t row0 = 0;
         for (size_t c : {(size_t)8, (size_t)4, (size_t)2, (size_t)1}) {
             if (c == 8 && quant) continue;
+            if (c > 1 && k->prm.group_k) continue;  // the per-group-scale kernel is single-row: one pass per row of x
             while (M - row0 >= c) {
                 b200mm_kernel* child = nullptr;
                 b200mm_kernel_params prm = k->prm;
@@ -757,11 +760,10 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     const size_t group_k = k->prm.group_k;
     if (group_k) {  // per-(row block, column) scales stored behind the weights
         if (!quant) return fail(ctx, B200MM_ERR_INVALID, "group_k applies to qgemv_sint8 only");
-        if (M != 1) return fail(ctx, B200MM_ERR_INVALID, "qgemv_sint8 with group_k: M must be 1");
-        if (group_k % 128) return fail(ctx, B200MM_ERR_INVALID, "qgemv_sint8: group_k must be a multiple of 128 (got %zu)", group_k);
-        if (k->prm.flags & B200MM_F_PEER_STORE) return fail(ctx, B200MM_ERR_INVALID, "qgemv_sint8 with group_k: peer stores not supported");
+        if (group_k != 32 && group_k != 64 && group_k % 128)
+            return fail(ctx, B200MM_ERR_INVALID, "qgemv_sint8: group_k must be 32, 64 or a multiple of 128 (got %zu)", group_k);
     }
-    const GemvPick pick = quant ? gemv_pick<GemvS8>(k->gemv_variant, mrows, group_k != 0) : gemv_pick<GemvF32>(k->gemv_variant, mrows);
+    const GemvPick pick = quant ? gemv_pick<GemvS8>(k->gemv_variant, mrows, group_k) : gemv_pick<GemvF32>(k->gemv_variant, mrows);
     const GemvFn fn = pick.fn;
     const int warps = pick.warps, lpr = pick.lpr;
     const int panel = lpr * cols;
@@ -806,7 +808,7 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
         else
             splits = 8;
     }
-    const int rstep = group_k ? 128 : warps * (32 / lpr);  // grouped: splits start on a pipeline-window boundary
+    const int rstep = group_k ? (int)std::min<size_t>(group_k, 128) : warps * (32 / lpr);  // grouped: splits start on a pipeline-window boundary
     auto smem_for = [&](size_t rows) {
         size_t b = ((size_t)mrows * rows + (size_t)warps * mrows * panel + (size_t)8 * mrows * panel) * sizeof(float);  // x, warp partials, 8 cluster receive slots
         if (group_k) b += ((rows / group_k + 2) * panel + (size_t)warps * 32 * cols) * sizeof(float);  // scales + per-thread totals
@@ -1332,7 +1334,7 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
         case B200MM_K_GEMV_F32:
         case B200MM_K_QGEMV_SINT8: {
             const bool quant = k->id == B200MM_K_QGEMV_SINT8;
-            const GemvFn fn = (quant ? gemv_pick<GemvS8>(k->gemv_variant, (int)k->M, k->prm.group_k != 0) : gemv_pick<GemvF32>(k->gemv_variant, (int)k->M)).fn;
+            const GemvFn fn = (quant ? gemv_pick<GemvS8>(k->gemv_variant, (int)k->M, k->prm.group_k) : gemv_pick<GemvF32>(k->gemv_variant, (int)k->M)).fn;
             const size_t group_k = k->prm.group_k;
             const float scale = quant ? (group_k ? 1.0f : k->prm.absmax) / 127.0f : 1.0f;
             const size_t wstride = quant ? (size_t)K * N + (group_k ? ceil_div(K, group_k) * N * 4 : 0) : (size_t)K * N * 4;

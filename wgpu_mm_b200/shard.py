@@ -236,7 +236,7 @@ class ShardedGemv:
     nccl: local slice + all_gather_into_tensor (slices are contiguous)."""
 
     def __init__(self, ctx, K: int, N: int, plan: ShardPlan, quant: bool = False, mode: str = "fused", seed: int = 300,
-                 x_host=None, panel_host=None, absmax: float = 2.0, nsets: int = 1, deferred: bool = True, autotune: bool = True):
+                 x_host=None, panel_host=None, absmax: float = 2.0, nsets: int = 1, deferred: bool = True, autotune: bool = True, group_k: int = 0):
         import torch
         import torch.distributed as dist
         import wgpu_mm_b200 as w
@@ -269,7 +269,7 @@ class ShardedGemv:
         self.peers = []
         kid = w.KernelId.QGEMV_SINT8 if quant else w.KernelId.GEMV_F32
         # the per-rank panel is a small matrix: let the library measure the launch geometry once (B200MM_F_AUTOTUNE)
-        self.kern = ctx.kernel(kid, 1, Np, K, w.KernelParams(absmax=absmax, batch=1, flags=int(w.Flags.AUTOTUNE) if autotune else 0))
+        self.kern = ctx.kernel(kid, 1, Np, K, w.KernelParams(absmax=0.0 if group_k else absmax, batch=1, group_k=group_k, flags=int(w.Flags.AUTOTUNE) if autotune else 0))
         if mode == "fused":
             self.flags = ctx.buffer(64)
             self.flags.write(np.zeros(16, dtype=np.uint32))
