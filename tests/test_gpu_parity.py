@@ -322,8 +322,8 @@ def test_qgemv_sint8(gpu_ctx, oracle, kn, variant):
     assert oracle.max_abs_err(got, oracle.wgsl_qgemv_1(x, words, N, K, 2.0)) <= 1e-4
 
 
-@pytest.mark.parametrize("case", [("s8", 4096, 14336, 21, 2, 148), ("s8", 4096, 14336, 21, 1, 296), ("s8", 1024, 1024, 21, 2, 40), ("s8", 1000, 1040, 13, 2, 9),
-                                  ("s8", 512, 4096, 21, 4, 74), ("f32", 1024, 2048, 5, 2, 20), ("f32", 4096, 16384, 5, 4, 148), ("f32", 300, 260, 4, 1, 7)])
+@pytest.mark.parametrize("case", [("s8", 4096, 14336, 21, 2, 148), ("s8", 4096, 14336, 21, 1, 296), ("s8", 1024, 1024, 21, 2, 40), ("s8", 1000, 1040, 13, 2, 17),
+                                  ("s8", 512, 4096, 21, 4, 74), ("f32", 1024, 2048, 5, 2, 20), ("f32", 4096, 16384, 5, 4, 148), ("f32", 300, 260, 4, 1, 20)])
 def test_gemv_balanced_ragged_panels(gpu_ctx, oracle, case):
     """tune[3] = explicit panel count: the column groups are dealt evenly to that many (ragged) panels so that a grid can be sized
     to exactly one CTA slot per panel x split.  Same results as the natural partition, bit for bit per column (the row order of
@@ -349,8 +349,14 @@ def test_gemv_balanced_ragged_panels(gpu_ctx, oracle, case):
     kern.free()
     natural = _run(gpu_ctx, kid, x, B, 1, N, K, w.KernelParams(absmax=2.0, batch=1, tune=(variant, splits, 0, 0)), b_dtype=dt)
     assert np.array_equal(got, natural)
-    with pytest.raises(w.B200mmError):  # more column groups per panel than the instantiation is wide
-        gpu_ctx.kernel(kid, 1, N, K, w.KernelParams(absmax=2.0, batch=1, tune=(variant, splits, 0, 16)))
+
+
+def test_gemv_panel_count_must_fit_the_instantiation(gpu_ctx):
+    import wgpu_mm_b200 as w
+    with pytest.raises(w.B200mmError):  # 896 column groups on 16 panels = 56 per panel, the 128-column instantiation holds 8
+        gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 1, 14336, 4096, w.KernelParams(absmax=2.0, batch=1, tune=(21, 2, 0, 16)))
+    with pytest.raises(w.B200mmError):  # more panels than column groups
+        gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 1, 256, 4096, w.KernelParams(absmax=2.0, batch=1, tune=(21, 2, 0, 17)))
 
 
 def test_qgemv_true_absmax_and_extremes(gpu_ctx, oracle):
@@ -661,7 +667,7 @@ def test_qgemv_sint8_skinny_m(gpu_ctx, oracle, m, kn):
 
 def test_gemv_rejects_unsupported_m(gpu_ctx):
     """The GEMV kernels stop at 16 rows of x (above that the SGEMM kernels take over); batched / grouped / peer-store launches
-    keep to the natively instantiated row counts."""
+    keep to the natively instantiated row counts (per-group scales with M > 1 run one pass per row)."""
     import wgpu_mm_b200 as w
     with pytest.raises(w.B200mmError):
         gpu_ctx.kernel(w.KernelId.GEMV_F32, 17, 1024, 1024)
@@ -670,7 +676,7 @@ def test_gemv_rejects_unsupported_m(gpu_ctx):
     with pytest.raises(w.B200mmError):
         gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 3, 1024, 1024, w.KernelParams(absmax=2.0, batch=2))
     with pytest.raises(w.B200mmError):
-        gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 3, 1024, 1024, w.KernelParams(group_k=128))
+        gpu_ctx.kernel(w.KernelId.QGEMV_SINT8, 3, 1024, 1024, w.KernelParams(group_k=128, batch=2))
 
 
 @pytest.mark.parametrize("case", ["gemv_f32", "qgemv_sint8", "gemv_f32_m4", "sgemm_tc3x", "sgemm_simt"])

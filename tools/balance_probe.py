@@ -24,5 +24,5 @@ def run(K, N, splits, variant=0, panels=0):
 for K, N, sp in ((4096, 14336, 0), (4096, 18944, 4), (4096, 9472, 8), (4096, 37888, 2), (4096, 28672, 2), (4096, 14336, 8), (8192, 9472, 8)):
     run(K, N, sp)
 print("balanced ragged panels (variant 21 = 128-column panels, tune[3] = panel count):")
-for sp, panels in ((2, 148), (1, 296), (4, 74), (2, 112), (2, 144), (2, 152), (1, 224)):
+for sp, panels in ((2, 148), (1, 296), (2, 112), (2, 144), (2, 152), (1, 224), (4, 112)):
     run(4096, 14336, sp, 21, panels)
