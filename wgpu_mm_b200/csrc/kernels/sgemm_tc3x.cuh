@@ -465,10 +465,8 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         }
     }
     ptx::tc_fence_before();
-    if constexpr (CTA2)
-        ptx::cluster_sync_all();  // the peer's barriers are initialised and its TMEM allocated before anything is signalled remotely
-    else
-        __syncthreads();
+    __syncthreads();  // barrier inits and the TMEM slot are visible CTA-wide (also what compute-sanitizer racecheck understands)
+    if constexpr (CTA2) ptx::cluster_sync_all();  // ... and the peer's, before anything is signalled remotely
     ptx::tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
