@@ -1442,9 +1442,10 @@ extern "C" int b200mm_mm_host(b200mm_ctx* ctx, b200mm_kernel* kern, const void* 
         CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
         CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
     }
-    while ((int)ctx->pipe_ev.size() < 2 * 16 + 2) {
+    static const bool host_trace = getenv("B200MM_HOST_TRACE") != nullptr;  // debug: print the timeline of the pipelined call
+    while ((int)ctx->pipe_ev.size() < 3 * 16 + 2) {
         cudaEvent_t e;
-        CU_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU_TRY(ctx, cudaEventCreateWithFlags(&e, host_trace ? cudaEventDefault : cudaEventDisableTiming));
         ctx->pipe_ev.push_back(e);
     }
     if (!kern->panel || kern->panel_count != P) {
@@ -1495,9 +1496,21 @@ extern "C" int b200mm_mm_host(b200mm_ctx* ctx, b200mm_kernel* kern, const void* 
         CU_TRY(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->pipe_ev[2 + 16 + i], 0));
         CU_TRY(ctx, cudaMemcpyAsync((char*)hostC + (size_t)i * Mp * N * 4, (const char*)dC->ptr + (size_t)i * Mp * N * 4, Mp * N * 4,
                                     cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (host_trace) CU_TRY(ctx, cudaEventRecord(ctx->pipe_ev[2 + 32 + i], ctx->s_d2h));
     }
     CU_TRY(ctx, cudaStreamSynchronize(ctx->s_d2h));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (host_trace && !zero_copy_c) {
+        auto at = [&](cudaEvent_t e) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev_start, e);
+            return ms;
+        };
+        fprintf(stderr, "[b200mm] mm_host %zux%zux%zu, %d panels: B up %.3f ms |", M, N, K, P, at(ev_b));
+        for (int i = 0; i < P; ++i)
+            fprintf(stderr, " p%d: A up %.3f gemm done %.3f C down %.3f |", i, at(ctx->pipe_ev[2 + i]), at(ctx->pipe_ev[2 + 16 + i]), at(ctx->pipe_ev[2 + 32 + i]));
+        fprintf(stderr, "\n");
+    }
     return B200MM_OK;
 }
 
