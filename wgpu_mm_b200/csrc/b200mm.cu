@@ -473,6 +473,7 @@ static GemvPick gemv_pick(int variant, int mrows = 1, size_t grouped = 0) {
         if (variant == 12) return GEMV_INST(8, 4, 16, 1, false, 4);
         if (variant == 13) return GEMV_INST(8, 4, 16, 1, false, 1, 1);
         if (variant == 21) return GEMV_INST(8, 4, 8, 1, false, 1, 1);  // 128-column panels: the balanced (ragged-panel) grids, tune[3] = panel count
+        if (variant == 25) return GEMV_INST(8, 4, 4, 1, false, 1, 1);  // 64-column panels: small matrices (per-rank panels of an N-sharded run)
     } else {
         // skinny GEMM: only the default geometry of each weight type is instantiated for M = 2, 4, 8
         if (mrows == 2) return GEMV_INST(4, 4, 32, 2);
@@ -757,6 +758,13 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     // tune[0]: 0 = default for the weight type (measured on B200, tools/sweep_gemv.py), 100 = variant 0, else the variant id
     // sint8 default = 13: the 8-warp / 256-column geometry of variant 4 with both register buffers in flight (12.75 vs 13.45 us at cfg4)
     k->gemv_variant = k->prm.tune[0] == 0 ? (quant ? 13 : 5) : (k->prm.tune[0] == 100 ? 0 : (int)k->prm.tune[0]);
+    if (k->prm.tune[0] == 0 && quant && !k->prm.group_k && M == 1) {
+        // small sint8 matrices (e.g. the per-rank panels of an N-sharded run): with 256-column panels x 8 K-splits there are fewer
+        // CTAs than SMs and too few bytes in flight -- take the widest panel that still yields a CTA per SM (measured, tools/small_s8.py:
+        // 4096 x 1792: 7.4 -> 4.5 us with 64-column panels; 4096 x 3584: 7.7 -> 5.6 us with 128-column panels)
+        const size_t sms = (size_t)ctx->prop.multiProcessorCount;
+        if (ceil_div(N, 256) * 8 < sms) k->gemv_variant = ceil_div(N, 128) * 8 >= sms ? 21 : 25;
+    }
     const size_t group_k = k->prm.group_k;
     if (group_k) {  // per-(row block, column) scales stored behind the weights
         if (!quant) return fail(ctx, B200MM_ERR_INVALID, "group_k applies to qgemv_sint8 only");
@@ -887,10 +895,10 @@ static int gemv_autotune(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     // small fp32 matrices (the per-rank panels of an N-sharded run: 32 MiB at 8 GPUs) are short of bytes in flight with the
     // 128-column panels of the large-matrix geometries: the 64-column (16-lane) instantiations double the CTA count
     static const int f32_variants[] = {5, 100, 2, 3, 1, 4, 6, 7};
-    static const int s8_variants[] = {4, 11, 12, 13};
+    static const int s8_variants[] = {4, 11, 12, 13, 21, 25};  // the last two (narrow panels = more CTAs) only for small matrices
     static const int s8g_variants[] = {4, 11, 12, 14};
     const int* variants = quant ? (group_k ? s8g_variants : s8_variants) : f32_variants;
-    const int nvar = quant ? 4 : (wbytes <= ((size_t)96 << 20) ? 8 : 4);
+    const int nvar = quant ? ((!group_k && wbytes <= ((size_t)24 << 20)) ? 6 : 4) : (wbytes <= ((size_t)96 << 20) ? 8 : 4);
     const uint64_t launches_before = ctx->launches;
     float best_ms = 1e30f, default_ms = 1e30f;
     uint32_t best_v = 0, best_s = 0;
