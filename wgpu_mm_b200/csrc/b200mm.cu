@@ -760,10 +760,15 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     k->gemv_variant = k->prm.tune[0] == 0 ? (quant ? 13 : 5) : (k->prm.tune[0] == 100 ? 0 : (int)k->prm.tune[0]);
     if (k->prm.tune[0] == 0 && quant && !k->prm.group_k && M == 1) {
         // small sint8 matrices (e.g. the per-rank panels of an N-sharded run): with 256-column panels x 8 K-splits there are fewer
-        // CTAs than SMs and too few bytes in flight -- take the widest panel that still yields a CTA per SM (measured, tools/small_s8.py:
+        // CTAs than SMs and too few bytes in flight -- take the widest panel that still yields a CTA per SM (measured, tools/small_gemv.py:
         // 4096 x 1792: 7.4 -> 4.5 us with 64-column panels; 4096 x 3584: 7.7 -> 5.6 us with 128-column panels)
         const size_t sms = (size_t)ctx->prop.multiProcessorCount;
         if (ceil_div(N, 256) * 8 < sms) k->gemv_variant = ceil_div(N, 128) * 8 >= sms ? 21 : 25;
+    }
+    if (k->prm.tune[0] == 0 && !quant && M == 1) {
+        // same for small fp32 matrices: 64-column panels on 8 warps instead of 128-column panels on 4 (4096 x 2048: 14.4 -> 7.7 us)
+        // (tools/small_gemv.py: 4096 x 2048 14.4 -> 7.7 us, 4096 x 4096 15.7 -> 12.0 us)
+        if (ceil_div(N, 128) * 8 < (size_t)ctx->prop.multiProcessorCount * 2) k->gemv_variant = N <= 1024 ? 4 : 7;
     }
     const size_t group_k = k->prm.group_k;
     if (group_k) {  // per-(row block, column) scales stored behind the weights
