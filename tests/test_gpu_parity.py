@@ -216,6 +216,28 @@ def test_split_k_fixup_survives_a_busy_device(gpu_ctx, oracle, kid_name):
     hog.free(); kern.free(); other.close()
 
 
+def test_sgemm_tc3x_const_b_reuses_the_split_only_while_b_stays(gpu_ctx, oracle):
+    """B200MM_F_CONST_B (weights): B's tf32 lo part is computed on the first launch with a given B buffer and reused while the
+    pointer stays the same; a different B buffer must be split again.  Results are bit-identical to the unflagged kernel."""
+    import wgpu_mm_b200 as w
+    M, N, K = 256, 512, 384
+    A1, A2 = oracle.generate_weight_data(31, M, K), oracle.generate_weight_data(32, M, K)
+    B1, B2 = oracle.generate_weight_data(33, K, N), oracle.generate_weight_data(34, K, N)
+    plain = gpu_ctx.kernel(w.KernelId.SGEMM_TC3X, M, N, K)
+    const = gpu_ctx.kernel(w.KernelId.SGEMM_TC3X, M, N, K, w.KernelParams(flags=int(w.Flags.CONST_B)))
+    dA1, dA2, dB1, dB2 = (gpu_ctx.buffer_from(x) for x in (A1, A2, B1, B2))
+    dC, dR = gpu_ctx.buffer(M * N * 4), gpu_ctx.buffer(M * N * 4)
+    for dA, dB, A, B in ((dA1, dB1, A1, B1), (dA2, dB1, A2, B1), (dA1, dB2, A1, B2), (dA2, dB2, A2, B2), (dA2, dB1, A2, B1)):
+        gpu_ctx.launch(const, dA, dB, dC)
+        gpu_ctx.launch(plain, dA, dB, dR)
+        got, ref = dC.read(np.float32).reshape(M, N), dR.read(np.float32).reshape(M, N)
+        assert np.array_equal(got, ref)
+        _check(oracle, got, A, B)
+    for b in (dA1, dA2, dB1, dB2, dC, dR):
+        b.free()
+    plain.free(); const.free()
+
+
 def test_sgemm_tc3x_padded_path_is_deterministic_and_leaves_neighbours_alone(gpu_ctx, oracle):
     """N % 4 != 0: C has an odd pitch; the copy-back must write exactly M x N floats (canary behind C) and repeat bit for bit."""
     import wgpu_mm_b200 as w
@@ -349,6 +371,25 @@ def test_gemv_balanced_ragged_panels(gpu_ctx, oracle, case):
     kern.free()
     natural = _run(gpu_ctx, kid, x, B, 1, N, K, w.KernelParams(absmax=2.0, batch=1, tune=(variant, splits, 0, 0)), b_dtype=dt)
     assert np.array_equal(got, natural)
+
+
+def test_peer_flags_need_peers_first(gpu_ctx):
+    """b200mm_kernel_set_peer_flags is only meaningful on a GEMV kernel that already has its peers (world >= 2)."""
+    import ctypes as C
+    import wgpu_mm_b200 as w
+    kern = gpu_ctx.kernel(w.KernelId.GEMV_F32, 1, 1024, 1024)
+    flags = gpu_ctx.buffer(64)
+    with pytest.raises(w.B200mmError):
+        kern.set_peer_flags([flags.ptr, flags.ptr], 0)
+    with pytest.raises(w.B200mmError):
+        kern.peer_wait()
+    gemm = gpu_ctx.kernel(w.KernelId.SGEMM_SIMT, 128, 128, 128)
+    with pytest.raises(w.B200mmError):
+        gemm.set_peer_flags([flags.ptr, flags.ptr], 0)
+    assert kern.peer_epoch == 0
+    for k in (kern, gemm):
+        k.free()
+    flags.free()
 
 
 def test_gemv_panel_count_must_fit_the_instantiation(gpu_ctx):
