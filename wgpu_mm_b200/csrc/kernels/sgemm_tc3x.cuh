@@ -9,17 +9,18 @@
 // A (M x K), B (K x N), C (M x N) row-major f32 (src/harness.rs:17-28 fixes the layout).
 //
 // Two kernels per GEMM:
-//   1. split_lo_kernel     elementwise pass, HBM-bound: reads A and B once, writes A_lo and B_lo
-//                          (kind::tf32 ignores the low 13 mantissa bits of its 32-bit operands: the raw operand
-//                          is consumed as hi, lo must be materialised);
-//   2. sgemm_tc3x_kernel   persistent, warp-specialised, 384 threads, one CTA per SM, tile 128 x BN x BK:
+//   1. split_lo_kernel     elementwise pass, HBM-bound: reads B and the FIRST row bands of A once, writes B_lo and that part of
+//                          A_lo (kind::tf32 ignores the low 13 mantissa bits of its 32-bit operands: the raw operand is
+//                          consumed as hi, lo must be materialised).  The later row bands of A are split inside kernel 2.
+//   2. sgemm_tc3x_kernel   persistent, warp-specialised, 384 threads, one CTA per SM, BK = 16:
 //        warp 0    TMA producer: per k-block loads A / A_lo (128 x BK, K-major, SWIZZLE_128B or _64B) and
 //                  B / B_lo (BK x BN, N-major: B is K x N row-major, so it is consumed as an MN-major
 //                  operand straight from its natural layout -- no transpose anywhere; a 3-D tensor map
 //                  (n%32, k, n/32) with SWIZZLE_128B_ATOM_32B lands the canonical MN-major atoms)
 //        warp 1    MMA issuer: one elected thread issues 3 x (BK/8) tcgen05.mma per k-block into a
-//                  128 x BN fp32 accumulator in TMEM; tcgen05.commit releases the smem stage
-//        warp 2    TMEM allocator
+//                  fp32 accumulator in TMEM; tcgen05.commit releases the smem stage
+//        warp 2    TMEM allocator, then SPLITTER: computes A_lo of the later 2048-row bands of A while earlier bands are being
+//                  multiplied (per-band ready counters, the producer waits on them; cooperative launch)
 //        warp 3    replicator (multi-GPU fused all-gather only): streams finished tiles to the peers over NVLink
 //        warps 4-11 epilogue (two warpgroups, one per column half): after every 256 k tcgen05.ld the finished
 //                  chain from TMEM and fold it into fp32 register accumulators with round-to-nearest adds (the
@@ -27,7 +28,10 @@
 //                  swizzled shared memory and store 128-byte row segments to C
 //      Two chain accumulators ping-pong in TMEM (2 x BN columns), so folding chain i overlaps the MMAs of
 //      chain i+1, across tile boundaries as well.  Tiles are scheduled in full waves plus a stream-K tail
-//      (Tc3xArgs) and rasterised in bands of 16 tile rows.
+//      (Tc3xArgs) and rasterised in bands of 2048 rows.
+//      Two instantiations: 128 x 256 tiles on single CTAs, and (Tc3xCfg::CTA2, the default for big GEMMs) 256 x 256 tiles on CTA
+//      PAIRS -- a cluster of two CTAs on one TPC, tcgen05 cta_group::2: each CTA stages its own 128 rows of A and half of the
+//      B tile, the pair's leader issues the MMAs for both tensor cores, each CTA drains its own accumulator.
 //
 // Roofline: tensor pipe.  Algorithmic work 2*M*N*K flop; the tensor pipe executes 3x that in TF32.
 #pragma once
