@@ -12,8 +12,12 @@ N > 1   workload = SGEMM 16384^3, B and C N-sharded over the ranks (BASELINE con
 One JSON line on stdout (rank 0).  `value` = whole-job TFLOP/s (2*M*N*K flop per step, FP32-equivalent)
 with inputs resident in HBM; `e2e` = the same metric through b200mm_mm_host with pinned HOST buffers
 (H2D of A and B and D2H of C inside the timed region); `roofline` is for the dominant kernel
-(sgemm_tc3x_kernel) timed by its own CUDA-event pair inside each step; `extras` carries the other
-BASELINE configs (SIMT SGEMM, fp32 GEMV, sint8 GEMV) measured the same way, each with its own roofline.
+(sgemm_tc3x_kernel) timed by its own CUDA-event pair inside each step, against peaks MEASURED in the same
+run (cuBLAS TF32, an FFMA2 microbenchmark: `extras.measured_peaks`); `extras` carries the other BASELINE
+configs (SIMT SGEMM, fp32 GEMV, sint8 GEMV -- each GEMV as a PDL stream, as cold single launches and end to
+end through host buffers), each with its own roofline.  Multi-GPU lines add `strong_scaling_base` (the same
+problem on one GPU of the same box), `verify` (every rank's C against FP64 / mm_ref, outside the timed
+region) and a non-redundant `e2e` (each byte crosses PCIe once).
 
 --impl reference times the reference's own CPU implementation of the path -- mm_ref, src/harness.rs:17-28,
 the code the reference crate itself executes on the host (its WGSL shaders need wgpu + a Vulkan ICD, absent
