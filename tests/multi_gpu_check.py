@@ -50,6 +50,27 @@ def main():
                   f"unwritten={unwritten} {'OK' if ok else 'FAIL'}", flush=True)
             failures += 0 if ok else 1
             job.close()
+    # ---- the 2-CTA pair kernel in fused mode: a per-rank panel with >= 74 pair tiles (10 x 8), whatever CHECK_SIZE is ----
+    Mp, Kp, Np_total = 2560, 512, 2048 * world
+    Ap = oracle.generate_weight_data(101, Mp, Kp)
+    Bp_full = oracle.generate_weight_data(102, Kp, Np_total)
+    prow = np.array(sorted({0, 127, 128, 255, 256, Mp // 2 + 3, Mp - 1}))
+    pref64 = oracle.mm_f64_rows(Ap, Bp_full, prow)
+    plan = shard.ShardPlan(Np_total, world, rank)
+    job = shard.ShardedSgemm(ctx, Mp, Np_total, Kp, plan, mode="fused", kernel_id=w.KernelId.SGEMM_TC3X, seed=100)
+    grid, _ = job.kern.geometry()
+    job.C.write(np.full(Mp * Np_total, 123.25, dtype=np.float32))
+    job.barrier()
+    for _ in range(2):
+        job.step()
+    job.barrier()
+    got = np.stack([job.C.read(np.float32, count=Np_total, offset=int(r) * Np_total * 4) for r in prow])
+    e, m = oracle.err_vs_f64(got, pref64)
+    unwritten = int((job.read_rows(range(0, Mp, 97)) == 123.25).sum())
+    ok = (e / m <= 5e-6) and unwritten == 0 and grid[0] % 2 == 0
+    print(f"rank {rank}/{world} mode=fused kernel=SGEMM_TC3X pair tiles (grid {grid[0]}): rel_f64={e / m:.3e} unwritten={unwritten} {'OK' if ok else 'FAIL'}", flush=True)
+    failures += 0 if ok else 1
+    job.close()
     # ---- N-sharded GEMV (fp32 and sint8 in the quant.rs format) ----
     Kv, Nv = 2048, 4096
     x = oracle.generate_weight_data(301, 1, Kv)
