@@ -140,6 +140,14 @@ class ShardedSgemm:
             self.dist.all_gather_into_tensor(self.G_t, self.Cp_t)
             self.ctx.unshard_columns(self.G_t.data_ptr(), self.C.ptr, self.M, self.N, self.plan.world)
 
+    def consumed(self):
+        """Call (stream-ordered) after this rank has finished READING C of the last step and before the next step() when the
+        operands change between steps: in fused mode a rank that is ahead would otherwise start storing the next step's tiles
+        into a peer's C while that peer still reads the previous result (write-after-read across ranks).  One peer-flag
+        barrier; the NCCL mode needs nothing (the gather writes C only after every rank has entered the collective)."""
+        if self.mode == "fused":
+            self.pbar()
+
     def barrier(self):
         self.ctx.sync()
         self.torch.cuda.synchronize()
