@@ -766,7 +766,7 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
         if (ceil_div(N, 256) * 8 < sms) k->gemv_variant = ceil_div(N, 128) * 8 >= sms ? 21 : 25;
     }
     if (k->prm.tune[0] == 0 && !quant && M == 1) {
-        // same for small fp32 matrices: 64-column panels on 8 warps instead of 128-column panels on 4 (4096 x 2048: 14.4 -> 7.7 us)
+        // same for small fp32 matrices: 64-column panels instead of 128-column ones
         // (tools/small_gemv.py: 4096 x 2048 14.4 -> 7.7 us, 4096 x 4096 15.7 -> 12.0 us)
         if (ceil_div(N, 128) * 8 < (size_t)ctx->prop.multiProcessorCount * 2) k->gemv_variant = N <= 1024 ? 4 : 7;
     }
