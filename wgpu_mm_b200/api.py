@@ -34,6 +34,12 @@ class KernelParams:
         return p
 
 
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    """Address of a numpy array's data.  `a.ctypes.data_as(...)` builds a helper object on every call (tens of microseconds --
+    measurable in the end-to-end timings of the microsecond-scale GEMV calls and even of mm_host); the array interface is a dict lookup."""
+    return C.c_void_p(a.__array_interface__["data"][0])
+
+
 class Context:
     """gpu_handle (src/harness.rs:87-101): one device, one in-order stream."""
 
@@ -89,7 +95,7 @@ class Context:
         """create_buffer_init (src/harness.rs:135,158)."""
         a = np.ascontiguousarray(array)
         h = C.c_void_p()
-        check(lib().b200mm_buffer_create_init(self._h, a.ctypes.data_as(C.c_void_p), a.nbytes, C.byref(h)), self._h)
+        check(lib().b200mm_buffer_create_init(self._h, _ptr(a), a.nbytes, C.byref(h)), self._h)
         return Buffer(self, h, a.nbytes)
 
     def wrap(self, device_ptr: int, nbytes: int) -> "Buffer":
@@ -118,8 +124,8 @@ class Context:
 
     def mm_host(self, kern: "Kernel", hostA: np.ndarray, hostB: np.ndarray, hostC: np.ndarray, dA: "Buffer", dB: "Buffer", dC: "Buffer"):
         """End-to-end call with host buffers: H2D(A,B) + launch + D2H(C), blocking."""
-        check(lib().b200mm_mm_host(self._h, kern.handle, hostA.ctypes.data_as(C.c_void_p), hostA.nbytes,
-                                   hostB.ctypes.data_as(C.c_void_p), hostB.nbytes, hostC.ctypes.data_as(C.c_void_p),
+        check(lib().b200mm_mm_host(self._h, kern.handle, _ptr(hostA), hostA.nbytes,
+                                   _ptr(hostB), hostB.nbytes, _ptr(hostC),
                                    hostC.nbytes, dA.handle, dB.handle, dC.handle), self._h)
 
     def timer_begin(self):
@@ -160,23 +166,23 @@ class Buffer:
         return lib().b200mm_buffer_device_ptr(self._h) or 0
 
     def write(self, array: np.ndarray, offset: int = 0):
-        a = np.ascontiguousarray(array)
-        check(lib().b200mm_buffer_write(self.ctx.handle, self._h, offset, a.ctypes.data_as(C.c_void_p), a.nbytes), self.ctx.handle)
+        a = array if (isinstance(array, np.ndarray) and array.flags.c_contiguous) else np.ascontiguousarray(array)
+        check(lib().b200mm_buffer_write(self.ctx.handle, self._h, offset, _ptr(a), a.nbytes), self.ctx.handle)
 
     def read(self, dtype=np.float32, count: Optional[int] = None, offset: int = 0) -> np.ndarray:
         """to_cpu (src/harness.rs:289-302): blocking read-back."""
         itemsize = np.dtype(dtype).itemsize
         n = count if count is not None else (self.nbytes - offset) // itemsize
         out = np.empty(n, dtype=dtype)
-        check(lib().b200mm_buffer_read(self.ctx.handle, self._h, offset, out.ctypes.data_as(C.c_void_p), out.nbytes), self.ctx.handle)
+        check(lib().b200mm_buffer_read(self.ctx.handle, self._h, offset, _ptr(out), out.nbytes), self.ctx.handle)
         return out
 
     def read_into(self, out: np.ndarray, offset: int = 0):
-        check(lib().b200mm_buffer_read(self.ctx.handle, self._h, offset, out.ctypes.data_as(C.c_void_p), out.nbytes), self.ctx.handle)
+        check(lib().b200mm_buffer_read(self.ctx.handle, self._h, offset, _ptr(out), out.nbytes), self.ctx.handle)
 
     def read_2d_into(self, out: np.ndarray, offset: int, src_pitch: int, width_bytes: int, rows: int):
         """Blocking read of `rows` rows of width_bytes (row r from offset + r*src_pitch) into the contiguous array `out`."""
-        check(lib().b200mm_buffer_read_2d(self.ctx.handle, self._h, offset, src_pitch, out.ctypes.data_as(C.c_void_p), width_bytes,
+        check(lib().b200mm_buffer_read_2d(self.ctx.handle, self._h, offset, src_pitch, _ptr(out), width_bytes,
                                           width_bytes, rows), self.ctx.handle)
 
     def fill_weights(self, seed: int, n: int, offset: int = 0):

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -1456,6 +1457,8 @@ extern "C" int b200mm_mm_host(b200mm_ctx* ctx, b200mm_kernel* kern, const void* 
         CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
     }
     static const bool host_trace = getenv("B200MM_HOST_TRACE") != nullptr;  // debug: print the timeline of the pipelined call
+    timespec ts_entry{}, ts_enq{}, ts_done{};
+    if (host_trace) clock_gettime(CLOCK_MONOTONIC, &ts_entry);
     while ((int)ctx->pipe_ev.size() < 3 * 16 + 2) {
         cudaEvent_t e;
         CU_TRY(ctx, cudaEventCreateWithFlags(&e, host_trace ? cudaEventDefault : cudaEventDisableTiming));
@@ -1511,9 +1514,14 @@ extern "C" int b200mm_mm_host(b200mm_ctx* ctx, b200mm_kernel* kern, const void* 
                                     cudaMemcpyDeviceToHost, ctx->s_d2h));
         if (host_trace) CU_TRY(ctx, cudaEventRecord(ctx->pipe_ev[2 + 32 + i], ctx->s_d2h));
     }
+    if (host_trace) clock_gettime(CLOCK_MONOTONIC, &ts_enq);
     CU_TRY(ctx, cudaStreamSynchronize(ctx->s_d2h));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (host_trace) clock_gettime(CLOCK_MONOTONIC, &ts_done);
     if (host_trace && !zero_copy_c) {
+        auto ms_between = [](const timespec& a, const timespec& b) { return (b.tv_sec - a.tv_sec) * 1e3 + (b.tv_nsec - a.tv_nsec) * 1e-6; };
+        fprintf(stderr, "[b200mm] mm_host host side: everything enqueued after %.3f ms, returned after %.3f ms\n", ms_between(ts_entry, ts_enq),
+                ms_between(ts_entry, ts_done));
         auto at = [&](cudaEvent_t e) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ev_start, e);
