@@ -325,7 +325,7 @@ def test_gemv_f32_split_k_is_deterministic(gpu_ctx, oracle, splits, cluster_off)
 QSHAPES = [(1024, 1024), (64, 64), (4096, 14336), (200, 48), (36, 16)]
 
 
-@pytest.mark.parametrize("variant", [0, 100, 1, 4, 5, 6, 11, 12, 13])
+@pytest.mark.parametrize("variant", [0, 100, 1, 4, 5, 6, 11, 12, 13, 21, 25])
 @pytest.mark.parametrize("kn", QSHAPES)
 def test_qgemv_sint8(gpu_ctx, oracle, kn, variant):
     """Quantised GEMV in the src/quant.rs format with the reference's ABSMAX = 2.0 quirk."""
