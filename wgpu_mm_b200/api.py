@@ -53,7 +53,11 @@ class Context:
             lib().b200mm_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: the module globals the loader needs may already be gone
+            pass
 
     def __enter__(self):
         return self
