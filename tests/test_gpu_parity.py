@@ -127,6 +127,9 @@ def test_sgemm_tc3x_cta_pairs(gpu_ctx, oracle, shape):
     _check(oracle, got, A, B)
     again = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K, w.KernelParams(tune=(512, 0, 0, 0)))
     assert np.array_equal(got, again)
+    # the st.global epilogue (tune[2] = 6) and the TMA-store epilogue (default) move the same values
+    stg = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K, w.KernelParams(tune=(512, 0, 6, 0)))
+    assert np.array_equal(got, stg)
     if K <= 256:  # one chain per tile: no K-split anywhere, so the two kernels perform the same arithmetic
         single = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K, w.KernelParams(tune=(513, 0, 0, 0)))
         assert np.array_equal(got, single)

@@ -45,6 +45,8 @@ def test_sass_contains_blackwell_instructions(built_lib):
     assert re.search(r"UTC\w*MMA", sass), "no tcgen05.mma in SASS"
     assert "UTMALDG" in sass, "no TMA tensor load in SASS"
     assert "LDTM" in sass, "no tcgen05.ld in SASS"
+    assert "UTMASTG" in sass, "no TMA tensor store in SASS (pair kernel epilogue)"
+    assert re.search(r"UTC\w*MMA\.2CTA", sass), "no cta_group::2 MMA in SASS"
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", w.lib_path()], capture_output=True, text=True).stdout
 
 

@@ -18,7 +18,7 @@ for i in range(nsets):
     b = ctx.buffer(K * N * 4); b.fill_weights(2 + 10 * i, K * N)
     c = ctx.buffer(M * N * 4)
     sets.append((a, b, c))
-variants = {"1cta": (513, 0), "2cta_bk16": (512, 0), "2cta_bk32": (512, 32)}
+variants = {"1cta": (513, 0), "2cta_tmast": (512, 0), "2cta_stg": (512, 6), "2cta_bk32": (512, 32)}  # tmast = TMA-store epilogue (default), stg = st.global epilogue
 kerns = {n: ctx.kernel(w.KernelId.SGEMM_TC3X, M, N, K, w.KernelParams(tune=(t0, 0, t2, 0))) for n, (t0, t2) in variants.items()}
 iters = max(3, int(os.environ.get("ITERS", "0")) or int(2e-2 / (2.0 * M * N * K / 250e12)) or 3)
 res = {n: [] for n in variants}

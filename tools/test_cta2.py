@@ -15,7 +15,7 @@ for (M, N, K) in shapes:
     a = ctx.buffer(M * K * 4); a.fill_weights(1, M * K)
     b = ctx.buffer(K * N * 4); b.fill_weights(2, K * N)
     outs, times = [], []
-    for tune0, bk in ((513, 0), (512, 0)) + (((512, 32),) if os.environ.get("BK32") else ()):
+    for tune0, bk in ((513, 0), (512, 6 if os.environ.get("STG") else 0)) + (((512, 32),) if os.environ.get("BK32") else ()):
         c = ctx.buffer_from(np.full(M * N, 7.0, dtype=np.float32))
         k = ctx.kernel(w.KernelId.SGEMM_TC3X, M, N, K, w.KernelParams(tune=(tune0, 0, bk, 0)))
         ctx.launch(k, a, b, c)

@@ -64,7 +64,9 @@ struct b200mm_kernel {
     // tc3x
     float *a_lo = nullptr, *b_lo = nullptr;  // lo parts of the operands (the raw operands are consumed as hi)
     float* b_hi = nullptr;                   // padded copy of B, only when N % 32 != 0
-    CUtensorMap tmAh{}, tmAl{}, tmBh{}, tmBl{};
+    CUtensorMap tmAh{}, tmAl{}, tmBh{}, tmBl{}, tmC{};
+    bool tc_tma_store = false;       // pair kernel with the TMA-store epilogue
+    const void* tc_c_src = nullptr;  // C the store map currently points at (with the peer set it was built for)
     int tc_bn = 256, tc_bk = 32;
     bool tc_cta2 = false;  // 2-CTA (cta_group::2) instantiation: 256 x 256 tiles on CTA pairs
     const void *tc_a_src = nullptr, *tc_b_src = nullptr;  // operands the hi tensor maps currently point at
@@ -403,6 +405,20 @@ static int make_tmap_mnmajor(b200mm_ctx* ctx, CUtensorMap* tm, const float* base
     return B200MM_OK;
 }
 
+// C (store side): rows x cols f32 with leading dimension ld, 32 x 32 boxes (128-byte rows), SWIZZLE_128B.
+static int make_tmap_c(b200mm_ctx* ctx, CUtensorMap* tm, float* base, size_t rows, size_t cols, size_t ld) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return fail(ctx, B200MM_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * sizeof(float)};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, B200MM_ERR_CUDA, "cuTensorMapEncodeTiled(C) failed: %d", (int)r);
+    return B200MM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel registry
 // ------------------------------------------------------------------------------------------------
@@ -430,6 +446,7 @@ extern "C" const char* b200mm_kernel_name(int id) {
 using Tc256 = Tc3xCfg<256, 2, false, 32>;     // 2 stages x 96 KB
 using Tc256k16 = Tc3xCfg<256, 4, false, 16>;  // 4 stages x 48 KB: same bytes in flight, finer refill granularity
 using Tc256k16x2 = Tc3xCfg<256, 6, false, 16, 256, true>;  // 2-CTA pairs: 256 x 256 tiles, 6 stages x 32 KB per CTA
+using Tc256k16x2s = Tc3xCfg<256, 5, false, 16, 256, true, true>;  // same with the TMA-store epilogue: 5 stages + 64 KB of staging (the default pair kernel; tune[2] = 6 selects the one above)
 using Tc256k32x2 = Tc3xCfg<256, 3, false, 32, 256, true>;  // same with BK = 32: 3 stages x 64 KB (tune[2] = 32; measured, not the default)
 using Tc128 = Tc3xCfg<128, 3, false, 32>;
 using Tc256x1 = Tc3xCfg<256, 4, true, 32>;
@@ -648,6 +665,8 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
         const bool want2 = k->prm.tune[0] == 512 || (k->prm.tune[0] == 0 && tiles2 >= ctx->prop.multiProcessorCount / 2 && getenv("B200MM_TC3X_1CTA") == nullptr);
         k->tc_cta2 = want2 && !one_pass && k->tc_bn == 256 && ctx->prop.multiProcessorCount % 2 == 0;
         if (k->tc_cta2) k->tc_bk = (k->prm.tune[2] == 32) ? 32 : 16;
+        // pair kernel: TMA-store epilogue (5 stages + double-buffered staging) unless tune[2] = 6 asks for the st.global one (6 stages)
+        k->tc_tma_store = k->tc_cta2 && k->tc_bk == 16 && k->prm.tune[2] != 6;
     }
     const int tile_m = k->tc_cta2 ? 256 : 128;
     // workspace: lo parts of both operands (the raw operands are consumed as hi); for N % 32 != 0 also a padded
@@ -702,7 +721,10 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     // the hi maps point at the caller's A and B and are (re)encoded at launch time
     k->grid = dim3(grid_x, 1, 1);
     k->block = dim3(Tc256::THREADS, 1, 1);
-    if (k->tc_cta2 && k->tc_bk == 32) {
+    if (k->tc_tma_store) {
+        k->smem = Tc256k16x2s::SMEM_BYTES;
+        CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc256k16x2s>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
+    } else if (k->tc_cta2 && k->tc_bk == 32) {
         k->smem = Tc256k32x2::SMEM_BYTES;
         CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc256k32x2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
     } else if (k->tc_cta2) {
@@ -1128,6 +1150,7 @@ extern "C" int b200mm_kernel_set_peers(b200mm_kernel* k, int rank, int world, vo
     if (world < 0 || world > 8 || rank < 0 || (world && rank >= world)) return fail(nullptr, B200MM_ERR_INVALID, "set_peers: bad rank/world");
     if (world && (ldc % 4 || col_offset % 4)) return fail(nullptr, B200MM_ERR_INVALID, "set_peers: ldc and col_offset must be multiples of 4");
     k->peers = PeerStore{};
+    k->tc_c_src = nullptr;  // the TMA store map addresses the local C of the peer set: rebuild it
     k->peers.world = world;
     k->peers.rank = rank;
     k->peers.ldc = ldc;
@@ -1215,7 +1238,7 @@ static cudaError_t launch_tc3x(b200mm_kernel* k, cudaStream_t s, const float* A,
         attr[1].val.clusterDim.z = 1;
         cfg.numAttrs = 2;
     }
-    return cudaLaunchKernelEx(&cfg, sgemm_tc3x_kernel<Cfg>, k->tmAh, k->tmAl, k->tmBh, k->tmBl, a);
+    return cudaLaunchKernelEx(&cfg, sgemm_tc3x_kernel<Cfg>, k->tmAh, k->tmAl, k->tmBh, k->tmBl, k->tmC, a);
 }
 
 extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* A, const void* B, void* C,
@@ -1331,7 +1354,16 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
                                                         skip_b ? 0 : b4);
                 ctx->launches += 1;
                 prof_begin();
-                if (k->tc_cta2 && k->tc_bk == 32)
+                if (k->tc_tma_store) {
+                    // store map: this rank's panel of the (local) C -- 32 x 32 boxes, SWIZZLE_128B; rebuilt when C moves
+                    float* cbase = k->peers.world ? k->peers.c[k->peers.rank] + k->peers.col0 : Cf;
+                    const size_t ldc = k->peers.world ? k->peers.ldc : k->N;
+                    if (k->tc_c_src != cbase) {
+                        if ((rc = make_tmap_c(ctx, &k->tmC, cbase, k->M, k->N, ldc))) return rc;
+                        k->tc_c_src = cbase;
+                    }
+                    le = launch_tc3x<Tc256k16x2s>(k, s, Af, Cf);
+                } else if (k->tc_cta2 && k->tc_bk == 32)
                     le = launch_tc3x<Tc256k32x2>(k, s, Af, Cf);
                 else if (k->tc_cta2)
                     le = launch_tc3x<Tc256k16x2>(k, s, Af, Cf);

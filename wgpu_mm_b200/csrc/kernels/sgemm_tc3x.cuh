@@ -173,6 +173,22 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// TMA store of one shared-memory box to global memory (bulk async-group completion); out-of-range parts of the box are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {  // at most N groups still READING their shared-memory source
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() {  // at most N groups not yet complete (writes visible)
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
 }
@@ -379,8 +395,14 @@ inline Tc3xSchedule tc3x_make_schedule(size_t M, size_t N, size_t K, int bn, int
 // own 128 rows of A and HALF of the B tile, the leader issues one MMA for both tensor cores, each CTA drains its own
 // 128 x BN accumulator.  Per SM and k-step that is 2 x (A 128 x BK + B BK x BN/2) instead of 2 x (A + B BK x BN): a third less
 // L2 -> shared-memory traffic and a third less operand reads per MMA -- energy, on a kernel that runs into the power cap.
-template <int BN_, int STAGES_, bool ONE_PASS_, int BK_ = 32, int CHAIN_K_ = 256, bool CTA2_ = false>
+// TMA_STORE: the epilogue hands each 32 x 32 chunk to the TMA (cp.async.bulk.tensor store, SASS UTMASTG) from a SWIZZLE_128B staging
+// buffer, double-buffered per warp, instead of eight st.global.v4 per lane: the LSU work of the store phase disappears from the warps
+// that have to be back in time to drain the next chain, and ragged edges are clipped by the tensor map.
+template <int BN_, int STAGES_, bool ONE_PASS_, int BK_ = 32, int CHAIN_K_ = 256, bool CTA2_ = false, bool TMA_STORE_ = false>
 struct Tc3xCfg {
+    static constexpr bool TMA_STORE = TMA_STORE_;
+    static constexpr int EPI_BUFS = TMA_STORE_ ? 2 : 1;
+    static constexpr uint32_t BAR_AREA = TMA_STORE_ ? 1024 : 256;  // barriers; the TMA staging behind it must be 1024-byte aligned
     static constexpr int BM = 128, BN = BN_, BK = BK_, STAGES = STAGES_, CHAIN = CHAIN_K_ / BK_;
     static constexpr bool CTA2 = CTA2_;
     static constexpr int TILE_M = CTA2 ? 256 : 128;   // rows of C per scheduled tile
@@ -398,8 +420,8 @@ struct Tc3xCfg {
     static constexpr uint32_t STAGE_BYTES = (ONE_PASS ? 1 : 2) * (A_BYTES + B_BYTES);
     static constexpr uint32_t TMEM_COLS = 2 * BN;              // two chain accumulators (ping-pong)
     static constexpr uint32_t EPI_STAGE_LD = 32;                                   // floats per staged row; 16 B chunks XOR-swizzled by row
-    static constexpr uint32_t EPI_STAGE_BYTES = EPI_WARPS * 32 * EPI_STAGE_LD * 4;  // one 32 x 32 chunk per epilogue warp
-    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
+    static constexpr uint32_t EPI_STAGE_BYTES = EPI_WARPS * EPI_BUFS * 32 * EPI_STAGE_LD * 4;  // 32 x 32 chunks per epilogue warp
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + BAR_AREA + EPI_STAGE_BYTES;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM cols: power of 2");
     static_assert(COLS_PER_WG % 32 == 0, "epilogue reads 32 columns per tcgen05.ld");
@@ -409,7 +431,7 @@ template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                  const __grid_constant__ Tc3xArgs p) {
+                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ Tc3xArgs p) {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, CHAIN = Cfg::CHAIN;
     constexpr bool ONE_PASS = Cfg::ONE_PASS, CTA2 = Cfg::CTA2;
     constexpr int TILE_M = Cfg::TILE_M, BN_CTA = Cfg::BN_CTA;
@@ -446,6 +468,7 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             ptx::prefetch_tmap(&tmAl);
             ptx::prefetch_tmap(&tmBl);
         }
+        if (Cfg::TMA_STORE) ptx::prefetch_tmap(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -754,9 +777,39 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
             // pieces of 32 different rows per instruction.  Instead every warp transposes 32 x 32 chunks through its own
             // 4 KB of shared memory (XOR-swizzled, conflict-free) so that each st.global.v4 covers 4 rows x 128 contiguous bytes -- full 128 B lines for
             // HBM and for NVLink when the tile also goes to the peers (fused all-gather).
-            float* stage = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw))) + (warp - 4) * 32 * Cfg::EPI_STAGE_LD;
+            float* stage = reinterpret_cast<float*>(smem_raw + (bar_base + Cfg::BAR_AREA - smem_u32(smem_raw))) + (warp - 4) * Cfg::EPI_BUFS * 32 * Cfg::EPI_STAGE_LD;
             const int row0 = tm * TILE_M + (int)cta_rank * BM + q * 32;
             const int col0 = tn * BN + half * COLS;
+            if constexpr (Cfg::TMA_STORE) {
+                // The staging layout (16-byte chunk j of row r at position j ^ (r & 7)) IS the TMA's SWIZZLE_128B pattern, so a chunk
+                // goes out as one 32 x 32 box; tmC addresses this rank's panel of the (local) C, out-of-range rows / columns are clipped.
+#pragma unroll  // must stay unrolled: acc[] is indexed with c and has to live in registers
+                for (int c = 0; c < COLS / 32; ++c) {
+                    float* buf = stage + (c & 1) * 32 * Cfg::EPI_STAGE_LD;
+                    if (lane == 0) ptx::bulk_wait_read<1>();  // the store that used this buffer two chunks ago has read it
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(buf + lane * Cfg::EPI_STAGE_LD + 4 * (j ^ (lane & 7))) =
+                            make_float4(acc[c * 32 + 4 * j], acc[c * 32 + 4 * j + 1], acc[c * 32 + 4 * j + 2], acc[c * 32 + 4 * j + 3]);
+                    ptx::fence_proxy_async();  // generic-proxy writes -> async-proxy (TMA) reads
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_2d(&tmC, smem_u32(buf), col0 + c * 32, row0);
+                        ptx::bulk_commit();
+                    }
+                }
+                if (p.peers.world > 1) {
+                    if (lane == 0) ptx::bulk_wait<0>();  // the tile is in (local) global memory before the replicator is told
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) {
+                        volatile unsigned int* td = tiles_done_ptr() + (warp - 4);
+                        *td = *td + 1u;  // single writer per counter
+                    }
+                }
+                continue;
+            }
             float* const base = p.peers.world == 0 ? p.C : p.peers.c[p.peers.rank];  // fused mode: local copy only, see replicator
             const size_t ld = p.peers.world == 0 ? (size_t)p.ldc : p.peers.ldc;
             const size_t coff = p.peers.world == 0 ? 0 : p.peers.col0;
@@ -788,6 +841,9 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
         }
     }
 
+    if constexpr (Cfg::TMA_STORE) {
+        if (warp >= 4 && lane == 0) ptx::bulk_wait_read<0>();  // shared memory must outlive the TMA stores that read it
+    }
     ptx::tc_fence_before();
     if constexpr (CTA2)
         ptx::cluster_sync_all();  // neither CTA may free TMEM / exit while the pair's MMAs or remote arrives are in flight
