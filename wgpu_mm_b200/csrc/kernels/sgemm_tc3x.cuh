@@ -31,7 +31,8 @@
 //      (Tc3xArgs) and rasterised in bands of 2048 rows.
 //      Two instantiations: 128 x 256 tiles on single CTAs, and (Tc3xCfg::CTA2, the default for big GEMMs) 256 x 256 tiles on CTA
 //      PAIRS -- a cluster of two CTAs on one TPC, tcgen05 cta_group::2: each CTA stages its own 128 rows of A and half of the
-//      B tile, the pair's leader issues the MMAs for both tensor cores, each CTA drains its own accumulator.
+//      B tile, the pair's leader issues the MMAs for both tensor cores, each CTA drains its own accumulator and hands its C chunks
+//      to the TMA (cp.async.bulk.tensor store from SWIZZLE_128B staging).
 //
 // Roofline: tensor pipe.  Algorithmic work 2*M*N*K flop; the tensor pipe executes 3x that in TF32.
 #pragma once
