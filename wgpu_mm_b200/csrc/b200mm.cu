@@ -1226,11 +1226,18 @@ static cudaError_t launch_tc3x(b200mm_kernel* k, cudaStream_t s, const float* A,
     cfg.blockDim = k->block;
     cfg.dynamicSmemBytes = k->smem;
     cfg.stream = s;
+    static const bool pdl_off = getenv("B200MM_TC3X_NO_PDL") != nullptr;  // experiment knob
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = (k->tc_prebands < k->tc_bands) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (!attr[0].val.cooperative && !pdl_off) {
+        // not cooperative (no in-kernel split): launch programmatically dependent on the split pass instead, so that the GEMM's
+        // prologue overlaps its tail (the kernel waits in griddepcontrol.wait before it touches any operand)
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+    }
     if constexpr (Cfg::CTA2) {  // CTA pairs: a cluster of two CTAs is placed on one TPC
         attr[1].id = cudaLaunchAttributeClusterDimension;
         attr[1].val.clusterDim.x = 2;

@@ -63,6 +63,9 @@ __device__ __forceinline__ float4 split_lo4(const float4& v) { return make_float
 // split INSIDE sgemm_tc3x_kernel by an otherwise idle warp per CTA while earlier bands are being multiplied (Tc3xArgs::split).
 __global__ void split_lo_kernel(const float4* __restrict__ a, float4* __restrict__ a_lo, size_t a4,
                                 const float4* __restrict__ b, float4* __restrict__ b_lo, size_t b4) {
+    // programmatic dependent launch: the GEMM that follows may become resident and run its prologue (tensor-map fetch, barrier
+    // init, TMEM allocation) while this pass is still streaming; it touches nothing of ours before its griddepcontrol.wait
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < a4 + b4; i += stride) {
@@ -498,6 +501,10 @@ sgemm_tc3x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
     ptx::tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    // Everything above is independent of earlier work on the stream; from here on the roles read the operands (and A_lo / B_lo from
+    // the split pass that precedes this launch) and write C and the workspace.  No-op unless launched with programmatic
+    // stream serialization (the host does that for the non-cooperative launches).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // tile order: grouped rasterisation.  Tiles are walked m-fastest inside bands of GROUP_M tile rows, band after
     // band, so the ~148 tiles in flight form a 16 x ~9 block and share 16 A panels + ~9 B panels in L2.  (Plain
