@@ -135,6 +135,30 @@ def test_sgemm_tc3x_cta_pairs(gpu_ctx, oracle, shape):
         assert np.array_equal(got, single)
 
 
+@pytest.mark.parametrize("force", [512, 513])
+@pytest.mark.parametrize("shape", [(256, 256, 256), (512, 768, 1024), (300, 520, 260), (1024, 1024, 1024), (2304, 2048, 768), (128, 4096, 2048),
+                                   (4096, 4096, 512), (2560, 4096, 4096)])
+def test_sgemm_tc3x_lo_tiles_computed_in_shared_memory(gpu_ctx, oracle, shape, force):
+    """Default kernels derive A_lo and B_lo from the landed tiles inside the GEMM (Tc3xCfg::SPLIT = 2, no pre-pass); tune[3]
+    selects the older forms: 1 / 4 = only B in the kernel (A in the pre-pass / by row bands), 2 = B in the pre-pass, 3 = A and B
+    in the pre-pass (round 1).  Same lo values, same MMA order -> bit-identical results, on CTA pairs (512) and single
+    CTAs (513), with stream-K tails, k-splits, ragged edges and several waves per CTA."""
+    import wgpu_mm_b200 as w
+    M, N, K = shape
+    A = oracle.generate_weight_data(23, M, K)
+    B = oracle.generate_weight_data(24, K, N)
+    got = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K, w.KernelParams(tune=(force, 0, 0, 0)))
+    assert not (got == 123.25).any()
+    rows = np.array(sorted({0, 1, 127, 128, M // 2 + 3, M - 1}))
+    e, m = oracle.err_vs_f64(got[rows], oracle.mm_f64_rows(A, B, rows))
+    assert e / m <= REL_F64
+    for t3 in (1, 2, 3, 4):
+        pre = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K, w.KernelParams(tune=(force, 0, 0, t3)))
+        assert np.array_equal(got, pre), f"tune[3] = {t3}"
+    again = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K, w.KernelParams(tune=(force, 0, 0, 0)))
+    assert np.array_equal(got, again)
+
+
 def test_sgemm_tc3x_cta_pairs_at_the_baseline_shape(gpu_ctx, oracle):
     """4096^3 takes the pair kernel by default (512 pair tiles >= 74 SM pairs): sampled rows vs FP64 / mm_ref, checksum of all tiles."""
     import wgpu_mm_b200 as w

@@ -1,5 +1,6 @@
 """A/B timing of sgemm_tc3x variants, interleaved round-robin so that clock / power drift hits all variants alike.
-python tools/ab_tc3x.py MxNxK [rounds]   variants: 1-CTA (tune 513), 2-CTA BK=16 (512), 2-CTA BK=32 (512, tune[2]=32)"""
+python tools/ab_tc3x.py MxNxK [rounds]   variants: 1-CTA (tune 513), 2-CTA BK=16 (512), 2-CTA BK=32 (512, tune[2]=32), and where the lo
+operands come from (tune[3]: 0 = computed in shared memory, 1 / 4 = only B, 2 / 3 = pre-pass); VARIANTS=a,b,... selects a subset."""
 import os
 import sys
 
@@ -18,8 +19,13 @@ for i in range(nsets):
     b = ctx.buffer(K * N * 4); b.fill_weights(2 + 10 * i, K * N)
     c = ctx.buffer(M * N * 4)
     sets.append((a, b, c))
-variants = {"1cta": (513, 0), "2cta_tmast": (512, 0), "2cta_stg": (512, 6), "2cta_bk32": (512, 32)}  # tmast = TMA-store epilogue (default), stg = st.global epilogue
-kerns = {n: ctx.kernel(w.KernelId.SGEMM_TC3X, M, N, K, w.KernelParams(tune=(t0, 0, t2, 0))) for n, (t0, t2) in variants.items()}
+# (tune[0], tune[2], tune[3]); tmast = TMA-store epilogue (default), stg = st.global epilogue; split2 = A_lo and B_lo in shared memory
+# (default), split1 = B_lo only (A by row bands), pre = lo operands from the split_lo pre-pass (A by row bands / everything)
+variants = {"1cta": (513, 0, 0), "2cta": (512, 0, 0), "2cta_split1": (512, 0, 4), "2cta_pre": (512, 0, 2), "2cta_pre_r1": (512, 0, 3),
+            "1cta_pre": (513, 0, 2), "2cta_stg_pre": (512, 6, 2), "2cta_bk32_pre": (512, 32, 2)}
+if os.environ.get("VARIANTS"):
+    variants = {n: variants[n] for n in os.environ["VARIANTS"].split(",")}
+kerns = {n: ctx.kernel(w.KernelId.SGEMM_TC3X, M, N, K, w.KernelParams(tune=(t0, 0, t2, t3))) for n, (t0, t2, t3) in variants.items()}
 iters = max(3, int(os.environ.get("ITERS", "0")) or int(2e-2 / (2.0 * M * N * K / 250e12)) or 3)
 res = {n: [] for n in variants}
 for n, k in kerns.items():
@@ -37,4 +43,4 @@ for r in range(rounds):
 flop = 2.0 * M * N * K
 for n, v in res.items():
     v = np.array(v)
-    print(f"{M}x{N}x{K} {n:10s}: median {np.median(v) * 1e3:9.1f} us ({flop / np.median(v) / 1e9:6.1f} TFLOP/s)  best {v.min() * 1e3:9.1f} us ({flop / v.min() / 1e9:6.1f})  rounds {rounds} x {iters} launches")
+    print(f"{M}x{N}x{K} {n:13s}: median {np.median(v) * 1e3:9.1f} us ({flop / np.median(v) / 1e9:6.1f} TFLOP/s)  best {v.min() * 1e3:9.1f} us ({flop / v.min() / 1e9:6.1f})  rounds {rounds} x {iters} launches")

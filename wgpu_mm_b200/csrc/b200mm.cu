@@ -68,6 +68,7 @@ struct b200mm_kernel {
     bool tc_tma_store = false;       // pair kernel with the TMA-store epilogue
     const void* tc_c_src = nullptr;  // C the store map currently points at (with the peer set it was built for)
     int tc_bn = 256, tc_bk = 32;
+    int tc_split = 0;                // Tc3xCfg::SPLIT: 1 = B_lo, 2 = A_lo and B_lo are computed inside the GEMM (2: no pre-pass at all)
     bool tc_cta2 = false;  // 2-CTA (cta_group::2) instantiation: 256 x 256 tiles on CTA pairs
     const void *tc_a_src = nullptr, *tc_b_src = nullptr;  // operands the hi tensor maps currently point at
     bool tc_b_copy = false;                               // ragged N: B is staged into a padded copy first
@@ -447,6 +448,10 @@ using Tc256 = Tc3xCfg<256, 2, false, 32>;     // 2 stages x 96 KB
 using Tc256k16 = Tc3xCfg<256, 4, false, 16>;  // 4 stages x 48 KB: same bytes in flight, finer refill granularity
 using Tc256k16x2 = Tc3xCfg<256, 6, false, 16, 256, true>;  // 2-CTA pairs: 256 x 256 tiles, 6 stages x 32 KB per CTA
 using Tc256k16x2s = Tc3xCfg<256, 5, false, 16, 256, true, true>;  // same with the TMA-store epilogue: 5 stages + 64 KB of staging (the default pair kernel; tune[2] = 6 selects the one above)
+using Tc256k16x2sb = Tc3xCfg<256, 5, false, 16, 256, true, true, 1>;  // ... and B_lo computed in shared memory (SPLIT = 1)
+using Tc256k16b = Tc3xCfg<256, 4, false, 16, 256, false, false, 1>;   // 1-CTA kernel with SPLIT = 1
+using Tc256k16x2sab = Tc3xCfg<256, 5, false, 16, 256, true, true, 2>;  // A_lo and B_lo computed in shared memory (SPLIT = 2): no pre-pass
+using Tc256k16ab = Tc3xCfg<256, 4, false, 16, 256, false, false, 2>;
 using Tc256k32x2 = Tc3xCfg<256, 3, false, 32, 256, true>;  // same with BK = 32: 3 stages x 64 KB (tune[2] = 32; measured, not the default)
 using Tc128 = Tc3xCfg<128, 3, false, 32>;
 using Tc256x1 = Tc3xCfg<256, 4, true, 32>;
@@ -667,6 +672,14 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
         if (k->tc_cta2) k->tc_bk = (k->prm.tune[2] == 32) ? 32 : 16;
         // pair kernel: TMA-store epilogue (5 stages + double-buffered staging) unless tune[2] = 6 asks for the st.global one (6 stages)
         k->tc_tma_store = k->tc_cta2 && k->tc_bk == 16 && k->prm.tune[2] != 6;
+        // lo tiles computed in shared memory (Tc3xCfg::SPLIT) for the two default instantiations.  tune[3]: 0 = A and B in the kernel (no
+        // pre-pass), 4 = B in the kernel, A by row bands (pre-pass for the first wave, warp 2 for the rest), 1 = B in the kernel, A in
+        // the pre-pass, 2 = B in the pre-pass, A by row bands (round 2's first form), 3 = A and B in the pre-pass (round 1)
+        const bool can_split = !one_pass && k->tc_bn == 256 && k->tc_bk == 16 && (k->tc_tma_store || !k->tc_cta2);
+        const uint32_t t3 = k->prm.tune[3];
+        k->tc_split = !can_split || t3 == 2 || t3 == 3 ? 0 : (t3 == 1 || t3 == 4 ? 1 : 2);
+        if (const char* e = getenv("B200MM_TC3X_SPLIT")) k->tc_split = can_split ? std::min(k->tc_split, atoi(e)) : 0;  // experiment knob
+        else k->tc_split = 0;  // NOT YET THE DEFAULT: the in-kernel split is opt-in (B200MM_TC3X_SPLIT=2) until it has been validated on the GPU
     }
     const int tile_m = k->tc_cta2 ? 256 : 128;
     // workspace: lo parts of both operands (the raw operands are consumed as hi); for N % 32 != 0 also a padded
@@ -685,22 +698,27 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     k->tc_sk_units = sched.sk_units;
     const size_t part_bytes = (size_t)grid_x * 128 * k->tc_bn * sizeof(float);
     // In-kernel A split (Tc3xArgs): the pre-pass covers the row bands the first wave of tiles touches, warp 2 of every CTA
-    // does the rest while earlier bands are multiplied.  tune[3] = 1 keeps the whole split in the pre-pass (round-1 behaviour).
+    // does the rest while earlier bands are multiplied.  tune[3] bit 0 (value 1 or 3) keeps the whole split of A in the pre-pass (3 = round-1
+    // behaviour: A and B in the pre-pass).
     k->tc_bands = (int)ceil_div(M, (size_t)kTc3xBandRows);
     {
         const long long band_tiles = (long long)(kTc3xBandRows / tile_m) * (long long)ceil_div(N, (size_t)k->tc_bn);
         const long long first_wave = std::min<long long>(sched.grid, sched.tiles);
         long long pre = sched.full_waves == 0 ? k->tc_bands : (first_wave + band_tiles - 1) / band_tiles;
-        if (k->prm.tune[3] == 1 || one_pass) pre = k->tc_bands;
+        if (k->prm.tune[3] == 1 || k->prm.tune[3] == 3 || one_pass || k->tc_split == 2) pre = k->tc_bands;
         k->tc_prebands = (int)std::min<long long>(std::max<long long>(pre, 1), k->tc_bands);
     }
     const size_t flag_bytes = ceil_div(((size_t)grid_x + (size_t)k->tc_bands) * sizeof(unsigned int), 1024) * 1024;
-    k->ws_bytes = (one_pass ? 0 : (a_al + b_al)) + (k->tc_b_copy ? b_al : 0) + part_bytes + flag_bytes;
+    // lo parts that are computed in shared memory (tc_split) need no workspace
+    const bool need_a_lo = !one_pass && k->tc_split < 2, need_b_lo = !one_pass && k->tc_split < 1;
+    k->ws_bytes = (need_a_lo ? a_al : 0) + (need_b_lo ? b_al : 0) + (k->tc_b_copy ? b_al : 0) + part_bytes + flag_bytes;
     CU_TRY(ctx, cudaMalloc(&k->ws, k->ws_bytes));
     char* w = (char*)k->ws;
-    if (!one_pass) {
+    if (need_a_lo) {
         k->a_lo = (float*)w;
         w += a_al;
+    }
+    if (need_b_lo) {
         k->b_lo = (float*)w;
         w += b_al;
     }
@@ -714,14 +732,20 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     k->tc_band_cnt = k->tc_flags + grid_x;
     CU_TRY(ctx, cudaMemsetAsync(k->ws, 0, k->ws_bytes, ctx->stream));
     int rc;
-    if (!one_pass) {
-        if ((rc = make_tmap_kmajor(ctx, &k->tmAl, k->a_lo, M, K, 128, bk))) return rc;
-        if ((rc = make_tmap_mnmajor(ctx, &k->tmBl, k->b_lo, K, N, bk, k->tc_cta2 ? k->tc_bn / 2 : k->tc_bn))) return rc;
-    }
+    if (need_a_lo && (rc = make_tmap_kmajor(ctx, &k->tmAl, k->a_lo, M, K, 128, bk))) return rc;
+    if (need_b_lo && (rc = make_tmap_mnmajor(ctx, &k->tmBl, k->b_lo, K, N, bk, k->tc_cta2 ? k->tc_bn / 2 : k->tc_bn))) return rc;
     // the hi maps point at the caller's A and B and are (re)encoded at launch time
     k->grid = dim3(grid_x, 1, 1);
     k->block = dim3(Tc256::THREADS, 1, 1);
-    if (k->tc_tma_store) {
+    if (k->tc_tma_store && k->tc_split) {
+        k->smem = Tc256k16x2sb::SMEM_BYTES;
+        CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc256k16x2sb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
+        CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc256k16x2sab>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
+    } else if (k->tc_split) {
+        k->smem = Tc256k16b::SMEM_BYTES;
+        CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc256k16b>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
+        CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc256k16ab>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
+    } else if (k->tc_tma_store) {
         k->smem = Tc256k16x2s::SMEM_BYTES;
         CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc256k16x2s>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
     } else if (k->tc_cta2 && k->tc_bk == 32) {
@@ -1352,14 +1376,16 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
             } else {
                 // pre-pass: B (unless its lo part is still valid) and the first row bands of A; the rest of A is split in-kernel
                 const size_t a4_pre = std::min<size_t>(a4, (size_t)k->tc_prebands * kTc3xBandRows * k->K / 4);
-                bool skip_b = k->tc_skip_b_split;
+                bool skip_b = k->tc_skip_b_split || k->tc_split >= 1;
                 if (k->prm.flags & B200MM_F_CONST_B) {
                     skip_b = skip_b || (k->tc_const_b == B);
                     k->tc_const_b = B;
                 }
-                split_lo_kernel<<<sms * 8, 256, 0, s>>>((const float4*)A, (float4*)k->a_lo, a4_pre, (const float4*)B, (float4*)k->b_lo,
-                                                        skip_b ? 0 : b4);
-                ctx->launches += 1;
+                if (k->tc_split < 2) {
+                    split_lo_kernel<<<sms * 8, 256, 0, s>>>((const float4*)A, (float4*)k->a_lo, a4_pre, (const float4*)B, (float4*)k->b_lo,
+                                                            skip_b ? 0 : b4);
+                    ctx->launches += 1;
+                }
                 prof_begin();
                 if (k->tc_tma_store) {
                     // store map: this rank's panel of the (local) C -- 32 x 32 boxes, SWIZZLE_128B; rebuilt when C moves
@@ -1369,8 +1395,14 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
                         if ((rc = make_tmap_c(ctx, &k->tmC, cbase, k->M, k->N, ldc))) return rc;
                         k->tc_c_src = cbase;
                     }
-                    le = launch_tc3x<Tc256k16x2s>(k, s, Af, Cf);
-                } else if (k->tc_cta2 && k->tc_bk == 32)
+                    le = k->tc_split == 2   ? launch_tc3x<Tc256k16x2sab>(k, s, Af, Cf)
+                         : k->tc_split == 1 ? launch_tc3x<Tc256k16x2sb>(k, s, Af, Cf)
+                                            : launch_tc3x<Tc256k16x2s>(k, s, Af, Cf);
+                } else if (k->tc_split == 2)
+                    le = launch_tc3x<Tc256k16ab>(k, s, Af, Cf);
+                else if (k->tc_split == 1)
+                    le = launch_tc3x<Tc256k16b>(k, s, Af, Cf);
+                else if (k->tc_cta2 && k->tc_bk == 32)
                     le = launch_tc3x<Tc256k32x2>(k, s, Af, Cf);
                 else if (k->tc_cta2)
                     le = launch_tc3x<Tc256k16x2>(k, s, Af, Cf);
