@@ -50,6 +50,24 @@ def test_sass_contains_blackwell_instructions(built_lib):
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", w.lib_path()], capture_output=True, text=True).stdout
 
 
+def test_sass_of_the_in_kernel_split(built_lib):
+    """Tc3xCfg::SPLIT = 2 (lo tiles computed in shared memory): the pair kernel issues TWO tensor loads per k-step (A, B) where
+    the pre-pass form issues four (A, A_lo, B, B_lo), and carries the LDS.128 / STS.128 of the split plus the 2-CTA MMA and the
+    TMA store."""
+    import wgpu_mm_b200 as w
+    sass = subprocess.run(["cuobjdump", "-sass", w.lib_path()], capture_output=True, text=True).stdout
+    fns = {}
+    for chunk in sass.split("Function : ")[1:]:
+        name = chunk.split("\n", 1)[0].strip()
+        if "sgemm_tc3x_kernel" in name:
+            fns[name] = chunk
+    pre = next(v for k, v in fns.items() if "Li256ELi5ELb0ELi16ELi256ELb1ELb1ELi0E" in k)
+    split2 = next(v for k, v in fns.items() if "Li256ELi5ELb0ELi16ELi256ELb1ELb1ELi2E" in k)
+    assert pre.count("UTMALDG") == 4 and split2.count("UTMALDG") == 2
+    assert "LDS.128" in split2 and "STS.128" in split2 and "LDS.128" not in pre
+    assert re.search(r"UTC\w*MMA\.2CTA", split2) and "UTMASTG" in split2
+
+
 def test_no_gpu_fails_loudly(built_lib):
     import wgpu_mm_b200 as w
     if w.device_count() > 0:

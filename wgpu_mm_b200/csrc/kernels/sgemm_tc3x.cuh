@@ -56,7 +56,16 @@ __device__ __forceinline__ float to_tf32_rna(float x) {
 // tools/probe_tc.py), so the raw fp32 operand already acts as hi = trunc(x) and only lo = tf32(x - trunc(x))
 // has to be materialised (x - trunc(x) is exact in fp32).  One launch covers A and B: reads 2 x 64 MB and
 // writes 2 x 64 MB at 4096^3 (a version that also materialised hi wrote 4 x 64 MB).
-__device__ __forceinline__ float split_lo1(float x) { return to_tf32_rna(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); }
+// The rounding of lo to tf32 is left to the consumer as well: adding half a tf32 ulp (bit 12) to the magnitude makes the tensor core's
+// truncation of the low 13 bits a round-to-nearest, ties away -- the value cvt.rna.tf32.f32 would produce -- in 3 instructions per
+// element instead of 5 (|x - hi| <= 2^-11 |x| cannot overflow; this code also runs inside the GEMM, Tc3xCfg::SPLIT).
+__device__ __forceinline__ float split_lo1(float x) {
+#ifdef B200MM_SPLIT_RNA_CVT
+    return to_tf32_rna(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
+#else
+    return __uint_as_float(__float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)) + 0x1000u);
+#endif
+}
 __device__ __forceinline__ float4 split_lo4(const float4& v) { return make_float4(split_lo1(v.x), split_lo1(v.y), split_lo1(v.z), split_lo1(v.w)); }
 
 // Only the first `a4` float4 of A are split here: the rows the first wave of tiles needs.  The remaining row bands of A are
