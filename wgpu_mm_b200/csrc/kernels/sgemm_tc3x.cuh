@@ -60,10 +60,10 @@ __device__ __forceinline__ float to_tf32_rna(float x) {
 // truncation of the low 13 bits a round-to-nearest, ties away -- the value cvt.rna.tf32.f32 would produce -- in 3 instructions per
 // element instead of 5 (|x - hi| <= 2^-11 |x| cannot overflow; this code also runs inside the GEMM, Tc3xCfg::SPLIT).
 __device__ __forceinline__ float split_lo1(float x) {
-#ifdef B200MM_SPLIT_RNA_CVT
-    return to_tf32_rna(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
-#else
+#ifdef B200MM_SPLIT_RNA_ADD
     return __uint_as_float(__float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)) + 0x1000u);
+#else
+    return to_tf32_rna(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));  // (the default until the add form is validated on the GPU)
 #endif
 }
 __device__ __forceinline__ float4 split_lo4(const float4& v) { return make_float4(split_lo1(v.x), split_lo1(v.y), split_lo1(v.z), split_lo1(v.w)); }
