@@ -139,23 +139,23 @@ def test_sgemm_tc3x_cta_pairs(gpu_ctx, oracle, shape):
 @pytest.mark.parametrize("shape", [(256, 256, 256), (512, 768, 1024), (300, 520, 260), (1024, 1024, 1024), (2304, 2048, 768), (128, 4096, 2048),
                                    (4096, 4096, 512), (2560, 4096, 4096)])
 def test_sgemm_tc3x_lo_tiles_computed_in_shared_memory(gpu_ctx, oracle, shape, force):
-    """Default kernels derive A_lo and B_lo from the landed tiles inside the GEMM (Tc3xCfg::SPLIT = 2, no pre-pass); tune[3]
-    selects the older forms: 1 / 4 = only B in the kernel (A in the pre-pass / by row bands), 2 = B in the pre-pass, 3 = A and B
-    in the pre-pass (round 1).  Same lo values, same MMA order -> bit-identical results, on CTA pairs (512) and single
-    CTAs (513), with stream-K tails, k-splits, ragged edges and several waves per CTA."""
+    """Tc3xCfg::SPLIT: the epilogue warps derive B_lo (tune[3] = 1, 4) or A_lo and B_lo (5: no pre-pass at all) from the landed
+    tiles inside the GEMM; 2 / 3 take the lo operands from the split_lo pre-pass (2: A by row bands, 3: round 1), 0 picks by shape.
+    Same lo values, same MMA order -> all forms are bit-identical, on CTA pairs (512) and single CTAs (513), with stream-K
+    tails, k-splits, ragged edges and several waves per CTA."""
     import wgpu_mm_b200 as w
     M, N, K = shape
     A = oracle.generate_weight_data(23, M, K)
     B = oracle.generate_weight_data(24, K, N)
-    got = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K, w.KernelParams(tune=(force, 0, 0, 0)))
+    got = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K, w.KernelParams(tune=(force, 0, 0, 5)))
     assert not (got == 123.25).any()
-    rows = np.array(sorted({0, 1, 127, 128, M // 2 + 3, M - 1}))
+    rows = np.array(sorted({0, 1, 127, min(128, M - 1), M // 2 + 3, M - 1}))
     e, m = oracle.err_vs_f64(got[rows], oracle.mm_f64_rows(A, B, rows))
     assert e / m <= REL_F64
-    for t3 in (1, 2, 3, 4):
-        pre = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K, w.KernelParams(tune=(force, 0, 0, t3)))
-        assert np.array_equal(got, pre), f"tune[3] = {t3}"
-    again = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K, w.KernelParams(tune=(force, 0, 0, 0)))
+    for t3 in (0, 1, 2, 3, 4):
+        other = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K, w.KernelParams(tune=(force, 0, 0, t3)))
+        assert np.array_equal(got, other), f"tune[3] = {t3}"
+    again = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K, w.KernelParams(tune=(force, 0, 0, 5)))
     assert np.array_equal(got, again)
 
 

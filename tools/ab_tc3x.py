@@ -1,6 +1,6 @@
 """A/B timing of sgemm_tc3x variants, interleaved round-robin so that clock / power drift hits all variants alike.
 python tools/ab_tc3x.py MxNxK [rounds]   variants: 1-CTA (tune 513), 2-CTA BK=16 (512), 2-CTA BK=32 (512, tune[2]=32), and where the lo
-operands come from (tune[3]: 0 = computed in shared memory, 1 / 4 = only B, 2 / 3 = pre-pass); VARIANTS=a,b,... selects a subset."""
+operands come from (tune[3]: 5 = computed in shared memory, 1 / 4 = only B, 2 / 3 = pre-pass, 0 = by shape); VARIANTS=a,b,... selects a subset."""
 import os
 import sys
 
@@ -19,10 +19,10 @@ for i in range(nsets):
     b = ctx.buffer(K * N * 4); b.fill_weights(2 + 10 * i, K * N)
     c = ctx.buffer(M * N * 4)
     sets.append((a, b, c))
-# (tune[0], tune[2], tune[3]); tmast = TMA-store epilogue (default), stg = st.global epilogue; split2 = A_lo and B_lo in shared memory
-# (default), split1 = B_lo only (A by row bands), pre = lo operands from the split_lo pre-pass (A by row bands / everything)
-variants = {"1cta": (513, 0, 0), "2cta": (512, 0, 0), "2cta_split1": (512, 0, 4), "2cta_pre": (512, 0, 2), "2cta_pre_r1": (512, 0, 3),
-            "1cta_pre": (513, 0, 2), "2cta_stg_pre": (512, 6, 2), "2cta_bk32_pre": (512, 32, 2)}
+# (tune[0], tune[2], tune[3]); default epilogue = TMA store, stg = st.global epilogue; split2 = A_lo and B_lo computed in shared memory,
+# split1 = B_lo only (A by row bands), no suffix = lo operands from the split_lo pre-pass (A by row bands; _r1: everything in the pre-pass)
+variants = {"1cta": (513, 0, 2), "2cta": (512, 0, 2), "2cta_split1": (512, 0, 4), "2cta_split2": (512, 0, 5), "2cta_r1": (512, 0, 3),
+            "1cta_split1": (513, 0, 4), "1cta_split2": (513, 0, 5), "2cta_stg": (512, 6, 2), "2cta_bk32": (512, 32, 2)}
 if os.environ.get("VARIANTS"):
     variants = {n: variants[n] for n in os.environ["VARIANTS"].split(",")}
 kerns = {n: ctx.kernel(w.KernelId.SGEMM_TC3X, M, N, K, w.KernelParams(tune=(t0, 0, t2, t3))) for n, (t0, t2, t3) in variants.items()}

@@ -17,7 +17,7 @@ ctx = w.Context(0)
 reps = int(os.environ.get("REPS", "2"))
 M = N = K = 4096
 sets = bench.make_sets(ctx, M, N, K, reps, 100)
-# TC3X_TUNE = "t0,t1,t2,t3": e.g. "0,0,0,1" keeps the whole operand split in the pre-pass, so the pair kernel is launched without the
+# TC3X_TUNE = "t0,t1,t2,t3": e.g. "0,0,0,3" keeps the whole operand split in the pre-pass, so the pair kernel is launched without the
 # cooperative attribute (ncu's kernel replay refused the cluster + cooperative launch: LaunchFailed after 2 passes); "513,0,0,0" = 1-CTA kernel
 tc_tune = tuple(int(v) for v in os.environ.get("TC3X_TUNE", "0,0,0,0").split(","))
 for kid in (w.KernelId.SGEMM_TC3X, w.KernelId.SGEMM_SIMT):

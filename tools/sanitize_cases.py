@@ -54,7 +54,9 @@ gemm(4224, 256, 512, (513, 0, 0, 0))         # 1-CTA kernel, 3 row bands: in-ker
 gemm(4352, 512, 256, (512, 0, 0, 0))         # pair kernel with the in-kernel A split
 gemm(512, 768, 1024, (512, 0, 0, 4))         # pair kernel, only B_lo computed in shared memory (A by row bands)
 gemm(4352, 512, 256, (513, 0, 0, 4))         # 1-CTA kernel, the same
-gemm(512, 768, 1024, (512, 0, 0, 2))         # pair kernel, lo operands from the pre-pass (the default above computes both in shared memory)
+gemm(512, 768, 1024, (512, 0, 0, 5))         # pair kernel, A_lo and B_lo computed in shared memory (no pre-pass)
+gemm(4224, 256, 512, (513, 0, 0, 5))         # 1-CTA kernel, the same
+gemm(128, 4096, 1024, (0, 0, 0, 0))          # skinny M: the shape rule picks B_lo in shared memory
 gemm(130, 66, 34, (0, 0, 0, 0))              # padded staging path (N % 4, K % 4 != 0)
 gemm(256, 256, 64, (0, 0, 0, 0), w.KernelId.SGEMM_SIMT)  # split-K with the inverted ownership
 gemv(1024, 1024, False)

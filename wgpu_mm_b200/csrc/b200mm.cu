@@ -68,6 +68,7 @@ struct b200mm_kernel {
     bool tc_tma_store = false;       // pair kernel with the TMA-store epilogue
     const void* tc_c_src = nullptr;  // C the store map currently points at (with the peer set it was built for)
     int tc_bn = 256, tc_bk = 32;
+    bool tc_a_prepass = false;       // the whole of A is split by the pre-pass (no row bands in the kernel)
     int tc_split = 0;                // Tc3xCfg::SPLIT: 1 = B_lo, 2 = A_lo and B_lo are computed inside the GEMM (2: no pre-pass at all)
     bool tc_cta2 = false;  // 2-CTA (cta_group::2) instantiation: 256 x 256 tiles on CTA pairs
     const void *tc_a_src = nullptr, *tc_b_src = nullptr;  // operands the hi tensor maps currently point at
@@ -672,14 +673,18 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
         if (k->tc_cta2) k->tc_bk = (k->prm.tune[2] == 32) ? 32 : 16;
         // pair kernel: TMA-store epilogue (5 stages + double-buffered staging) unless tune[2] = 6 asks for the st.global one (6 stages)
         k->tc_tma_store = k->tc_cta2 && k->tc_bk == 16 && k->prm.tune[2] != 6;
-        // lo tiles computed in shared memory (Tc3xCfg::SPLIT) for the two default instantiations.  tune[3]: 0 = A and B in the kernel (no
-        // pre-pass), 4 = B in the kernel, A by row bands (pre-pass for the first wave, warp 2 for the rest), 1 = B in the kernel, A in
-        // the pre-pass, 2 = B in the pre-pass, A by row bands (round 2's first form), 3 = A and B in the pre-pass (round 1)
+        // lo tiles computed in shared memory (Tc3xCfg::SPLIT), available in the two default instantiations.  Measured
+        // (profiles/r2_split_shapes.log): it pays where the GEMM is bound by reading B -- skinny M: 128 x 14336 x 4096 165 -> 101 us --
+        // and costs where the tensor pipe is the bound, because the split's LDS / STS compete with the MMA's operand reads for
+        // shared-memory bandwidth (4096^3: 529 -> 554 us with B only, 607 us with A and B; 8192^3: +15 % / +64 %).
+        // tune[3]: 0 = that rule (M <= 256 and a B of >= 16 MB: B in the kernel, A -- small -- in the pre-pass; otherwise as 2),
+        // 1 = B in the kernel, A in the pre-pass, 2 = B in the pre-pass, A by row bands (pre-pass for the first wave, warp 2 for the
+        // rest), 3 = A and B in the pre-pass (round 1), 4 = B in the kernel, A by row bands, 5 = A and B in the kernel (no pre-pass)
         const bool can_split = !one_pass && k->tc_bn == 256 && k->tc_bk == 16 && (k->tc_tma_store || !k->tc_cta2);
-        const uint32_t t3 = k->prm.tune[3];
-        k->tc_split = !can_split || t3 == 2 || t3 == 3 ? 0 : (t3 == 1 || t3 == 4 ? 1 : 2);
-        if (const char* e = getenv("B200MM_TC3X_SPLIT")) k->tc_split = can_split ? std::min(k->tc_split, atoi(e)) : 0;  // experiment knob
-        else k->tc_split = 0;  // NOT YET THE DEFAULT: the in-kernel split is opt-in (B200MM_TC3X_SPLIT=2) until it has been validated on the GPU
+        uint32_t t3 = k->prm.tune[3];
+        if (t3 == 0) t3 = (can_split && M <= 256 && K * N >= ((size_t)4 << 20)) ? 1 : 2;
+        k->tc_split = !can_split ? 0 : (t3 == 1 || t3 == 4) ? 1 : (t3 == 5 ? 2 : 0);
+        k->tc_a_prepass = (t3 == 1 || t3 == 3);
     }
     const int tile_m = k->tc_cta2 ? 256 : 128;
     // workspace: lo parts of both operands (the raw operands are consumed as hi); for N % 32 != 0 also a padded
@@ -698,14 +703,13 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     k->tc_sk_units = sched.sk_units;
     const size_t part_bytes = (size_t)grid_x * 128 * k->tc_bn * sizeof(float);
     // In-kernel A split (Tc3xArgs): the pre-pass covers the row bands the first wave of tiles touches, warp 2 of every CTA
-    // does the rest while earlier bands are multiplied.  tune[3] bit 0 (value 1 or 3) keeps the whole split of A in the pre-pass (3 = round-1
-    // behaviour: A and B in the pre-pass).
+    // does the rest while earlier bands are multiplied (unless tune[3] asks for the whole of A in the pre-pass, see above).
     k->tc_bands = (int)ceil_div(M, (size_t)kTc3xBandRows);
     {
         const long long band_tiles = (long long)(kTc3xBandRows / tile_m) * (long long)ceil_div(N, (size_t)k->tc_bn);
         const long long first_wave = std::min<long long>(sched.grid, sched.tiles);
         long long pre = sched.full_waves == 0 ? k->tc_bands : (first_wave + band_tiles - 1) / band_tiles;
-        if (k->prm.tune[3] == 1 || k->prm.tune[3] == 3 || one_pass || k->tc_split == 2) pre = k->tc_bands;
+        if (k->tc_a_prepass || one_pass || k->tc_split == 2) pre = k->tc_bands;
         k->tc_prebands = (int)std::min<long long>(std::max<long long>(pre, 1), k->tc_bands);
     }
     const size_t flag_bytes = ceil_div(((size_t)grid_x + (size_t)k->tc_bands) * sizeof(unsigned int), 1024) * 1024;
