@@ -81,7 +81,12 @@ typedef struct b200mm_kernel_params {
     float absmax;               /* dequant scale for the quantised kernels ("absmax", src/gemv.rs:30)        */
     uint32_t batch;             /* qgemv: number of (x, W, y) problems along global_id.y (qgemv_1.wgsl:12-14) */
     uint32_t flags;             /* B200MM_F_* below                                                            */
-    uint32_t tune[4];           /* kernel-specific tuning knobs; 0 = default                                  */
+    uint32_t tune[4];           /* kernel-specific tuning knobs; 0 = default.  Results never depend on them beyond the summation order.
+                                 * SGEMM_TC3X: [0] 128 / 256 = tile columns, 512 / 513 = force CTA pairs / single CTAs; [1] 1 = pure stream-K;
+                                 *   [2] 32 = BK 32, 6 = st.global epilogue on pairs; [3] where the tf32 lo operands come from: 1 / 4 = B_lo
+                                 *   computed in shared memory (default for M <= 256), 5 = A_lo and B_lo, 2 / 3 = split pre-pass (default otherwise).
+                                 * GEMV_F32 / QGEMV_SINT8: [0] instantiation, [1] K-splits, [2] 1 = no programmatic dependent launch (W written
+                                 *   by the preceding kernel), [3] 1 = no cluster reduction, >= 16 = number of column panels.           */
     uint32_t group_k;           /* qgemv_sint8 only: rows per quantisation group: 32, 64 or a multiple of 128; 0 = the reference's one
                                  * global absmax (src/quant.rs:17).  When > 0, B holds the K*N int8 weights followed by
                                  * ceil(K/group_k)*N f32 scales (per group and column) and `absmax` is ignored: SURVEY 8f rank 3. */
