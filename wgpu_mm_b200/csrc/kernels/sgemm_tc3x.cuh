@@ -26,6 +26,8 @@
 //                  chain from TMEM and fold it into fp32 register accumulators with round-to-nearest adds (the
 //                  tensor core's own accumulation truncates); at the end of the tile transpose through
 //                  swizzled shared memory and store 128-byte row segments to C
+//                  With Tc3xCfg::SPLIT the same warps also derive the lo tiles from the landed hi tiles in shared memory
+//                  (split_try: a cooperative job done wherever they would otherwise wait) -- the default for skinny M
 //      Two chain accumulators ping-pong in TMEM (2 x BN columns), so folding chain i overlaps the MMAs of
 //      chain i+1, across tile boundaries as well.  Tiles are scheduled in full waves plus a stream-K tail
 //      (Tc3xArgs) and rasterised in bands of 2048 rows.
