@@ -661,9 +661,16 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     }
     const bool one_pass = (k->prm.flags & B200MM_F_TC3X_1X) != 0;
     k->tc_bn = (k->prm.tune[0] == 128) ? 128 : 256;
+    // Small problems (tune[0] = 0): 128 x 128 tiles when even those leave no SM without a tile (twice the tiles, so half the k-slices
+    // per tile to reach one CTA per SM and half the fix-up traffic) and B is small.  Measured (tools/small_bn.py,
+    // profiles/r2_small_bn.log): 1024^3 31.7 -> 24.3 us, 512^3 22.6 -> 16.2 us, 4096 x 512 x 512 26.9 -> 18.5 us; from 2048^3 on, and
+    // for skinny M against a big B (128 x 14336 x 4096: 90 vs 167 us), the 256-column tiles win.
+    if (k->prm.tune[0] == 0 && !one_pass && ceil_div(M, 128) * ceil_div(N, 256) * 2 <= (size_t)ctx->prop.multiProcessorCount &&
+        K * N <= ((size_t)8 << 20))
+        k->tc_bn = 128;
     k->tc_bk = (k->prm.tune[2] == 32) ? 32 : 16;  // default: BK = 16, 4 stages
     if (one_pass) k->tc_bn = 256;
-    if (one_pass || k->tc_bn == 128) k->tc_bk = 32;
+    if (one_pass || k->tc_bn == 128) k->tc_bk = 32;  // (128 x 128 tiles with BK = 16, 6 stages: measured 8-20 % slower than BK = 32)
     // tune[0] = 512: the 2-CTA kernel (256 x 256 tiles on CTA pairs, cta_group::2); 513: force the 1-CTA kernel.  Default: pairs when
     // there are at least as many 256-row tiles as SM pairs (big GEMMs), single CTAs otherwise (skinny M: a pair would idle one SM).
     {
