@@ -669,6 +669,29 @@ def test_mm_host_end_to_end(gpu_ctx, oracle, kid_name, size):
     kern.free()
 
 
+def test_mm_host_with_ragged_n_and_k_then_device_launch(gpu_ctx, oracle):
+    """The pipelined host path on a shape whose kernel object owns an inner (zero-padded) kernel: N % 4 != 0, K % 4 != 0 with
+    M = 2 x 256 rows.  mm_host must leave that object intact -- a device-buffer launch and the free afterwards used to hit a
+    kernel that the panel set-up had freed."""
+    import wgpu_mm_b200 as w
+    M, N, K = 512, 1001, 515
+    A = oracle.generate_weight_data(44, M, K)
+    B = oracle.generate_weight_data(45, K, N)
+    Cm = np.full((M, N), 123.25, dtype=np.float32)
+    kern = gpu_ctx.kernel(w.KernelId.SGEMM_TC3X, M, N, K)
+    dA, dB, dC = gpu_ctx.buffer(M * K * 4), gpu_ctx.buffer(K * N * 4), gpu_ctx.buffer(M * N * 4)
+    gpu_ctx.mm_host(kern, A, B, Cm, dA, dB, dC)
+    _check(oracle, Cm, A, B)
+    dA2, dB2 = gpu_ctx.buffer_from(A), gpu_ctx.buffer_from(B)
+    dC2 = gpu_ctx.buffer_from(np.full(M * N, 123.25, dtype=np.float32))
+    gpu_ctx.launch(kern, dA2, dB2, dC2)
+    got = dC2.read(np.float32).reshape(M, N)
+    _check(oracle, got, A, B)  # (not bit-equal to Cm: the 256-row panels have their own k-split schedule)
+    for b in (dA, dB, dC, dA2, dB2, dC2):
+        b.free()
+    kern.free()
+
+
 @pytest.mark.parametrize("quant", [False, True])
 def test_gemv_dependent_chain_with_pdl(gpu_ctx, oracle, quant):
     """x_{i+1} = y_i through the same square weight matrix, 24 launches back to back.  The GEMV kernels are launched with

@@ -1548,10 +1548,10 @@ extern "C" int b200mm_mm_host(b200mm_ctx* ctx, b200mm_kernel* kern, const void* 
     }
     if (!kern->panel || kern->panel_count != P) {
         if (kern->panel) b200mm_kernel_free(ctx, kern->panel);
-    if (kern->inner) b200mm_kernel_free(ctx, kern->inner);
-    for (auto& c : kern->chunks) b200mm_kernel_free(ctx, c.kern);
         kern->panel = nullptr;
         b200mm_kernel_params prm = kern->prm;
+        // the panels share one B: its lo part is computed once (panel 0) and reused, so the pre-pass form is the cheaper one here
+        if (kern->id == B200MM_K_SGEMM_TC3X && prm.tune[3] == 0) prm.tune[3] = 2;
         if ((rc = b200mm_kernel_get(ctx, kern->id, M / P, N, K, &prm, &kern->panel))) return rc;
         kern->panel_count = P;
     }
