@@ -455,6 +455,7 @@ using Tc256k16x2sab = Tc3xCfg<256, 5, false, 16, 256, true, true, 2>;  // A_lo a
 using Tc256k16ab = Tc3xCfg<256, 4, false, 16, 256, false, false, 2>;
 using Tc256k32x2 = Tc3xCfg<256, 3, false, 32, 256, true>;  // same with BK = 32: 3 stages x 64 KB (tune[2] = 32; measured, not the default)
 using Tc128 = Tc3xCfg<128, 3, false, 32>;
+using Tc128b = Tc3xCfg<128, 3, false, 32, 256, false, false, 1>;  // 128 x 128 tiles with B_lo computed in shared memory
 using Tc256x1 = Tc3xCfg<256, 4, true, 32>;
 
 // Streaming-GEMV instantiations (template arguments: warps, unroll, lanes per row segment, rows of x, grouped scales,
@@ -665,9 +666,13 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     // per tile to reach one CTA per SM and half the fix-up traffic) and B is small.  Measured (tools/small_bn.py,
     // profiles/r2_small_bn.log): 1024^3 31.7 -> 24.3 us, 512^3 22.6 -> 16.2 us, 4096 x 512 x 512 26.9 -> 18.5 us; from 2048^3 on, and
     // for skinny M against a big B (128 x 14336 x 4096: 90 vs 167 us), the 256-column tiles win.
-    if (k->prm.tune[0] == 0 && !one_pass && ceil_div(M, 128) * ceil_div(N, 256) * 2 <= (size_t)ctx->prop.multiProcessorCount &&
-        K * N <= ((size_t)8 << 20))
-        k->tc_bn = 128;
+    // Against a big B the narrow tiles still pay when there are so few 256-column tiles that each would be cut into >= 8 k-slices
+    // (<= SMs / 8 tiles: skinny M with N <= 4096) -- together with B_lo computed in shared memory, see tc_split below:
+    // 128 x 4096 x 4096 54.7 -> 39.2 us, 16 x 4096 x 4096 51.3 -> 37.6 us.
+    {
+        const size_t tiles256 = ceil_div(M, 128) * ceil_div(N, 256), sms = (size_t)ctx->prop.multiProcessorCount;
+        if (k->prm.tune[0] == 0 && !one_pass && tiles256 * 2 <= sms && (K * N <= ((size_t)8 << 20) || tiles256 * 8 <= sms)) k->tc_bn = 128;
+    }
     k->tc_bk = (k->prm.tune[2] == 32) ? 32 : 16;  // default: BK = 16, 4 stages
     if (one_pass) k->tc_bn = 256;
     if (one_pass || k->tc_bn == 128) k->tc_bk = 32;  // (128 x 128 tiles with BK = 16, 6 stages: measured 8-20 % slower than BK = 32)
@@ -687,10 +692,10 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
         // tune[3]: 0 = that rule (M <= 256 and a B of >= 16 MB: B in the kernel, A -- small -- in the pre-pass; otherwise as 2),
         // 1 = B in the kernel, A in the pre-pass, 2 = B in the pre-pass, A by row bands (pre-pass for the first wave, warp 2 for the
         // rest), 3 = A and B in the pre-pass (round 1), 4 = B in the kernel, A by row bands, 5 = A and B in the kernel (no pre-pass)
-        const bool can_split = !one_pass && k->tc_bn == 256 && k->tc_bk == 16 && (k->tc_tma_store || !k->tc_cta2);
+        const bool can_split = !one_pass && ((k->tc_bn == 256 && k->tc_bk == 16 && (k->tc_tma_store || !k->tc_cta2)) || k->tc_bn == 128);
         uint32_t t3 = k->prm.tune[3];
         if (t3 == 0) t3 = (can_split && M <= 256 && K * N >= ((size_t)4 << 20)) ? 1 : 2;
-        k->tc_split = !can_split ? 0 : (t3 == 1 || t3 == 4) ? 1 : (t3 == 5 ? 2 : 0);
+        k->tc_split = !can_split ? 0 : (t3 == 1 || t3 == 4) ? 1 : (t3 == 5 ? (k->tc_bn == 128 ? 1 : 2) : 0);
         k->tc_a_prepass = (t3 == 1 || t3 == 3);
     }
     const int tile_m = k->tc_cta2 ? 256 : 128;
@@ -752,6 +757,9 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
         k->smem = Tc256k16x2sb::SMEM_BYTES;
         CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc256k16x2sb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
         CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc256k16x2sab>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
+    } else if (k->tc_split && k->tc_bn == 128) {
+        k->smem = Tc128b::SMEM_BYTES;
+        CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc128b>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
     } else if (k->tc_split) {
         k->smem = Tc256k16b::SMEM_BYTES;
         CU_TRY(ctx, cudaFuncSetAttribute(sgemm_tc3x_kernel<Tc256k16b>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem));
@@ -1409,7 +1417,9 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
                     le = k->tc_split == 2   ? launch_tc3x<Tc256k16x2sab>(k, s, Af, Cf)
                          : k->tc_split == 1 ? launch_tc3x<Tc256k16x2sb>(k, s, Af, Cf)
                                             : launch_tc3x<Tc256k16x2s>(k, s, Af, Cf);
-                } else if (k->tc_split == 2)
+                } else if (k->tc_split && k->tc_bn == 128)
+                    le = launch_tc3x<Tc128b>(k, s, Af, Cf);
+                else if (k->tc_split == 2)
                     le = launch_tc3x<Tc256k16ab>(k, s, Af, Cf);
                 else if (k->tc_split == 1)
                     le = launch_tc3x<Tc256k16b>(k, s, Af, Cf);
