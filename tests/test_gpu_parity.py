@@ -191,7 +191,8 @@ def test_sgemm_tc3x_ragged(gpu_ctx, oracle, shape):
     _check(oracle, got, A, B)
 
 
-@pytest.mark.parametrize("shape", [(4096, 4096, 512), (4096, 14336, 512), (19000, 256, 512), (4224, 4096, 768), (2048, 2048, 256)])
+@pytest.mark.parametrize("shape", [(4096, 4096, 512), (4096, 14336, 512), (19000, 256, 512), (4224, 4096, 768), (2048, 2048, 256),
+                                   (1792, 1792, 1792), (2304, 2304, 2304), (2560, 2048, 2560)])  # the last three: L2-resident stream-K / two-tile schedules
 def test_sgemm_tc3x_stream_k_tail_with_idle_ctas(gpu_ctx, oracle, shape):
     """Shapes whose stream-K tail has fewer units than CTAs (some CTAs get an empty range) or exactly one chain per tile:
     the round-1 fix-up spun forever on a CTA that never publishes (ADVICE r1, 4096 x 4096 x 512).  Sampled rows vs FP64

@@ -209,7 +209,8 @@ def test_grouped_codec_zero_group_and_asserts():
 
 
 TC3X_SHAPES = [(4096, 4096, 4096), (16384, 2048, 16384), (128, 4096, 4096), (256, 4096, 4096), (512, 4096, 4096), (1024, 4096, 4096),
-               (2048, 4096, 4096), (1000, 520, 300), (128, 256, 256), (128, 128, 16), (4096, 4096, 100), (300, 36, 4100), (19000, 256, 512)]
+               (2048, 4096, 4096), (1000, 520, 300), (128, 256, 256), (128, 128, 16), (4096, 4096, 100), (300, 36, 4100), (19000, 256, 512),
+               (1792, 1792, 1792), (2304, 2304, 2304), (2560, 2560, 2560), (2048, 4096, 2048)]  # L2-resident: stream-K instead of idle SMs / tiny tails
 
 
 @pytest.mark.parametrize("shape", TC3X_SHAPES)
@@ -278,6 +279,12 @@ def test_tc3x_schedule_reference_points():
     assert list(out)[:5] == [128, 0, 16, 4, 32]  # the 256-row panels of the host-buffer path: 32 tiles x 4 k-slices
     lib().b200mm_tc3x_schedule(1024, 4096, 4096, 256, 16, 148, 0, out)
     assert list(out)[:5] == [128, 1, 16, 1, 128]  # one tile per CTA, in lock-step
+    lib().b200mm_tc3x_schedule(1792, 1792, 1792, 512, 16, 148, 0, out)
+    assert list(out) == [74, 0, 7, 0, 49, 49 * 7]  # 49 pair tiles of 7 chains: no k-split divides, operands fit in L2 -> stream-K over all pairs
+    lib().b200mm_tc3x_schedule(2304, 2304, 2304, 512, 16, 148, 0, out)
+    assert list(out) == [74, 0, 9, 0, 81, 81 * 9]  # 81 pair tiles = one wave + 7, L2-resident: no whole wave, stream-K over everything
+    lib().b200mm_tc3x_schedule(2048, 2048, 2048, 512, 16, 148, 0, out)
+    assert list(out)[:5] == [64, 1, 8, 1, 64]  # 64 pair tiles for 74 pairs = 86 % of the machine: one whole tile per pair, no stream-K
     assert lib().b200mm_tc3x_schedule(0, 4096, 4096, 256, 16, 148, 0, out) != 0
     assert lib().b200mm_tc3x_schedule(128, 128, 128, 192, 16, 148, 0, out) != 0
 

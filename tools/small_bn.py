@@ -11,7 +11,7 @@ ctx = w.Context(0)
 shapes = [(n, n, n) for n in (256, 512, 768, 1024, 1280, 1536, 2048, 2560)] if len(sys.argv) < 2 else [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]]
 for (M, N, K) in shapes:
     sets = bench.make_sets(ctx, M, N, K, 3, 100)
-    kerns = {name: ctx.kernel(w.KernelId.SGEMM_TC3X, M, N, K, w.KernelParams(tune=t)) for name, t in (("default", (0, 0, 0, 0)), ("bn256", (513, 0, 0, 0)), ("bn128", (128, 0, 0, 2)), ("bn128_split1", (128, 0, 0, 1)), ("simt", None)) if t}
+    kerns = {name: ctx.kernel(w.KernelId.SGEMM_TC3X, M, N, K, w.KernelParams(tune=t)) for name, t in (("default", (0, 0, 0, 0)), ("bn256", (513, 0, 0, 0)), ("bn128", (128, 0, 0, 2)), ("bn128_split1", (128, 0, 0, 1)), ("streamk", (513, 1, 0, 0)), ("pair", (512, 0, 0, 0)), ("pair_streamk", (512, 1, 0, 0)), ("simt", None)) if t}
     kerns["simt"] = ctx.kernel(w.KernelId.SGEMM_SIMT, M, N, K)
     res = {k: [] for k in kerns}
     for r in range(5):

@@ -680,7 +680,11 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     // there are at least as many 256-row tiles as SM pairs (big GEMMs), single CTAs otherwise (skinny M: a pair would idle one SM).
     {
         const long long tiles2 = (long long)ceil_div(M, 256) * (long long)ceil_div(N, 256);
-        const bool want2 = k->prm.tune[0] == 512 || (k->prm.tune[0] == 0 && tiles2 >= ctx->prop.multiProcessorCount / 2 && getenv("B200MM_TC3X_1CTA") == nullptr);
+        // (L2-resident problems run as stream-K over all SMs whatever the tile count -- tc3x_make_schedule -- so pairs pay from
+        // about 2/3 of a wave on: 1792^3 63.3 -> 60.9 us, 2048^3 79.5 -> 76.1 us)
+        const bool fits_l2 = 8.0 * ((double)M * (double)K + (double)K * (double)N) <= 100e6;
+        const long long min_tiles2 = fits_l2 ? 48 : ctx->prop.multiProcessorCount / 2;
+        const bool want2 = k->prm.tune[0] == 512 || (k->prm.tune[0] == 0 && tiles2 >= min_tiles2 && getenv("B200MM_TC3X_1CTA") == nullptr);
         k->tc_cta2 = want2 && !one_pass && k->tc_bn == 256 && ctx->prop.multiProcessorCount % 2 == 0;
         if (k->tc_cta2) k->tc_bk = (k->prm.tune[2] == 32) ? 32 : 16;
         // pair kernel: TMA-store epilogue (5 stages + double-buffered staging) unless tune[2] = 6 asks for the st.global one (6 stages)

@@ -403,6 +403,8 @@ inline Tc3xSchedule tc3x_make_schedule(size_t M, size_t N, size_t K, int bn, int
     sc.tiles = (long long)((M + tile_m - 1) / tile_m) * (long long)((N + bn - 1) / bn);
     // hybrid schedule: whole-tile waves while there is >= one tile per SM, stream-K over the remainder
     long long grid = sc.tiles * sc.chains_per_tile < sms ? sc.tiles * sc.chains_per_tile : sms;
+    // hi and lo parts of both operands against the 126 MB L2 (with room for C and the workspace)
+    const bool fits_l2 = 8.0 * ((double)M * (double)K + (double)K * (double)N) <= 100e6;
     if (sc.tiles < sms && !pure_stream_k) {
         // Fewer tiles than SMs (skinny M, and the row panels of the pipelined host-buffer path): plain stream-K gives every CTA a
         // k-range that starts somewhere else, so CTAs that share an A row panel or a B column panel are never at the same k and
@@ -414,9 +416,22 @@ inline Tc3xSchedule tc3x_make_schedule(size_t M, size_t N, size_t K, int bn, int
             if (sc.chains_per_tile % d == 0 && sc.tiles * d <= sms) S = d;
         grid = sc.tiles * S;
         sc.k_split = S;
+        // ... unless that leaves more than a fifth of the SMs idle (no admissible divisor: 1792^3 has 49 pair tiles of 7 chains for 74
+        // SM pairs) AND the operands fit in L2, where de-synchronised k positions cost nothing: then plain stream-K over all SMs
+        // (1792^3 68.3 -> 61.0 us).  Needs at least two chains of work per CTA to be worth the fix-ups.
+        if (fits_l2 && grid * 5 < (long long)sms * 4 && sc.tiles * sc.chains_per_tile >= 2LL * sms) {
+            grid = sms;
+            sc.k_split = 0;
+        }
     }
     sc.grid = (int)grid;
     sc.full_waves = pure_stream_k ? 0 : (int)(sc.tiles / grid);
+    // Whole waves exist to keep the CTAs in lock-step so that they share operand panels out of L2.  When the operands FIT in L2
+    // that is worth nothing, and a remainder wave only costs: 2304^3 has 81 pair tiles for 74 SM pairs -- 7 tiles cut into ten
+    // pieces each, every finisher adding ten parked parts one after the other.  L2-resident problems whose tile count is not a
+    // multiple of the grid therefore run as plain stream-K: between one and two tile boundaries per CTA, at most two contributors per
+    // tile (2304^3 127.3 -> 105 us, 2432 x 2432 x 1024 74.5 -> 65.6 us, 2560^3 150 -> 142 us).
+    if (!pure_stream_k && !sc.k_split && fits_l2 && sc.tiles % grid != 0) sc.full_waves = 0;
     sc.sk_units = (sc.tiles - (long long)sc.full_waves * grid) * sc.chains_per_tile;
     return sc;
 }
