@@ -214,6 +214,49 @@ def test_sgemm_tc3x_stream_k_tail_with_idle_ctas(gpu_ctx, oracle, shape):
     assert np.array_equal(got, again)
 
 
+def _random_tc3x_shapes(n, seed=2024):
+    """Seeded shapes across the regimes the default rules of setup_tc3x distinguish: 128- vs 256-column tiles, single CTAs vs pairs,
+    k-split vs stream-K vs whole waves, B_lo from the pre-pass vs computed in shared memory, ragged edges, the padded path."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        kind = i % 6
+        if kind == 0:    # small and squarish: 128 x 128 tiles
+            M, N, K = rng.integers(1, 1536), 4 * rng.integers(1, 384), 4 * rng.integers(1, 384)
+        elif kind == 1:  # skinny M against a big B: B_lo computed in shared memory
+            M, N, K = rng.integers(1, 257), 4 * rng.integers(512, 1025), 4 * rng.integers(1024, 1537)
+        elif kind == 2:  # L2-resident mid sizes: stream-K, pairs from 48 pair tiles on
+            M, N, K = 4 * rng.integers(400, 640), 4 * rng.integers(400, 640), 4 * rng.integers(64, 512)
+        elif kind == 3:  # more than one wave of pair tiles
+            M, N, K = rng.integers(2500, 4200), 4 * rng.integers(700, 1050), 4 * rng.integers(32, 160)
+        elif kind == 4:  # N or K not a multiple of 4: zero-padded staging copies
+            M, N, K = rng.integers(1, 700), rng.integers(1, 900), rng.integers(1, 900)
+        else:            # tall and narrow
+            M, N, K = rng.integers(3000, 9000), 4 * rng.integers(1, 64), 4 * rng.integers(16, 256)
+        out.append((int(M), int(N), int(K)))
+    return out
+
+
+@pytest.mark.parametrize("shape", _random_tc3x_shapes(36))
+def test_sgemm_tc3x_default_rules_on_random_shapes(gpu_ctx, oracle, shape):
+    """Whatever instantiation and schedule the default rules pick: sampled rows against FP64 and mm_ref, the FP64 checksum of
+    checksums over ALL tiles, no unwritten element, and two launches bit-identical."""
+    import wgpu_mm_b200 as w
+    M, N, K = shape
+    A = oracle.generate_weight_data(61, M, K)
+    B = oracle.generate_weight_data(62, K, N)
+    got = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K)
+    assert not np.isnan(got).any() and not (got == 123.25).any()
+    rows = np.array(sorted({0, M // 3, M // 2, max(0, M - 129), M - 1}))
+    e, m = oracle.err_vs_f64(got[rows], oracle.mm_f64_rows(A, B, rows))
+    assert e / max(m, 1e-30) <= REL_F64
+    assert oracle.max_abs_err(got[rows], oracle.mm_ref(A[rows], B)) <= GATE
+    cs = A.astype(np.float64).sum(axis=0) @ B.astype(np.float64)
+    assert np.abs(got.astype(np.float64).sum(axis=0) - cs).max() <= 1e-6 * M * np.abs(cs).max() + 1e-3
+    again = _run(gpu_ctx, w.KernelId.SGEMM_TC3X, A, B, M, N, K)
+    assert np.array_equal(got, again)
+
+
 @pytest.mark.parametrize("kid_name", ["SGEMM_TC3X", "SGEMM_SIMT"])
 def test_split_k_fixup_survives_a_busy_device(gpu_ctx, oracle, kid_name):
     """The split-K / stream-K finisher only waits on lower-numbered CTAs, so it cannot deadlock when the grid is not fully
