@@ -71,6 +71,32 @@ def main():
     print(f"rank {rank}/{world} mode=fused kernel=SGEMM_TC3X pair tiles (grid {grid[0]}): rel_f64={e / m:.3e} unwritten={unwritten} {'OK' if ok else 'FAIL'}", flush=True)
     failures += 0 if ok else 1
     job.close()
+    # ---- skinny M in fused mode: each rank's 128 x 4096 x 4096 panel takes the 128 x 128-tile kernel that derives B_lo in shared
+    # memory (epilogue warps split while the replicator warp streams finished tiles to the peers) ----
+    Ms, Ks, Ns_total = 128, 4096, 4096 * world
+    plan = shard.ShardPlan(Ns_total, world, rank)
+    job = shard.ShardedSgemm(ctx, Ms, Ns_total, Ks, plan, mode="fused", kernel_id=w.KernelId.SGEMM_TC3X, seed=110)
+    job.C.write(np.full(Ms * Ns_total, 123.25, dtype=np.float32))
+    job.barrier()
+    for _ in range(2):
+        job.step()
+    job.barrier()
+    got = job.read_rows(range(Ms))
+    unwritten = int((got == 123.25).sum())
+    # own column panel against FP64 from the operands as they sit in this rank's HBM; the other panels through the cross-rank checksum
+    A_dev = job.A.read(np.float32).reshape(Ms, Ks)
+    B_dev = job.Bp.read(np.float32).reshape(Ks, plan.cols)
+    own = got[:, plan.col0:plan.col0 + plan.cols]
+    e, m = oracle.err_vs_f64(own, oracle.mm_f64(A_dev, B_dev))
+    cs = torch.from_numpy(np.ascontiguousarray(got.astype(np.float64).sum(axis=0))).cuda()
+    ref_cs = cs.clone()
+    dist.broadcast(ref_cs, src=0)  # all ranks must hold the same full C: compare the column sums with rank 0's
+    same = bool(torch.equal(cs, ref_cs))
+    ok = (e / m <= 5e-6) and unwritten == 0 and same
+    print(f"rank {rank}/{world} mode=fused kernel=SGEMM_TC3X skinny M=128 (grid {job.kern.geometry()[0][0]}): rel_f64={e / m:.3e} unwritten={unwritten} "
+          f"same_on_all_ranks={same} {'OK' if ok else 'FAIL'}", flush=True)
+    failures += 0 if ok else 1
+    job.close()
     # ---- N-sharded GEMV (fp32 and sint8 in the quant.rs format) ----
     Kv, Nv = 2048, 4096
     x = oracle.generate_weight_data(301, 1, Kv)
