@@ -680,11 +680,14 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     // there are at least as many 256-row tiles as SM pairs (big GEMMs), single CTAs otherwise (skinny M: a pair would idle one SM).
     {
         const long long tiles2 = (long long)ceil_div(M, 256) * (long long)ceil_div(N, 256);
-        // (L2-resident problems run as stream-K over all SMs whatever the tile count -- tc3x_make_schedule -- so pairs pay from
-        // about 2/3 of a wave on: 1792^3 63.3 -> 60.9 us, 2048^3 79.5 -> 76.1 us)
+        // (a tile count that would leave SMs idle runs as stream-K over all of them -- tc3x_make_schedule -- so pairs pay from about
+        // 2/3 of a wave on: 1792^3 63.3 -> 60.9 us, 2048^3 79.5 -> 76.1 us, 768 x 4096 x 4096 136 -> 129 us; not for a single row of
+        // pair tiles, M <= 256, where the skinny-M rules below decide)
         const bool fits_l2 = 8.0 * ((double)M * (double)K + (double)K * (double)N) <= 100e6;
-        const long long min_tiles2 = fits_l2 ? 48 : ctx->prop.multiProcessorCount / 2;
-        const bool want2 = k->prm.tune[0] == 512 || (k->prm.tune[0] == 0 && tiles2 >= min_tiles2 && getenv("B200MM_TC3X_1CTA") == nullptr);
+        const long long min_tiles2 = (fits_l2 || M >= 512) ? 48 : ctx->prop.multiProcessorCount / 2;
+        // 256-row tiles must not pad M much more than 128-row tiles would (640 rows: 768 vs 640 computed -- measured 126 vs 120 us)
+        const bool pad_ok = ceil_div(M, 256) * 256 == ceil_div(M, 128) * 128 || M >= 2048;
+        const bool want2 = k->prm.tune[0] == 512 || (k->prm.tune[0] == 0 && tiles2 >= min_tiles2 && pad_ok && getenv("B200MM_TC3X_1CTA") == nullptr);
         k->tc_cta2 = want2 && !one_pass && k->tc_bn == 256 && ctx->prop.multiProcessorCount % 2 == 0;
         if (k->tc_cta2) k->tc_bk = (k->prm.tune[2] == 32) ? 32 : 16;
         // pair kernel: TMA-store epilogue (5 stages + double-buffered staging) unless tune[2] = 6 asks for the st.global one (6 stages)

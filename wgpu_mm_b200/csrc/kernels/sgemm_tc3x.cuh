@@ -417,9 +417,10 @@ inline Tc3xSchedule tc3x_make_schedule(size_t M, size_t N, size_t K, int bn, int
         grid = sc.tiles * S;
         sc.k_split = S;
         // ... unless that leaves more than a fifth of the SMs idle (no admissible divisor: 1792^3 has 49 pair tiles of 7 chains for 74
-        // SM pairs) AND the operands fit in L2, where de-synchronised k positions cost nothing: then plain stream-K over all SMs
-        // (1792^3 68.3 -> 61.0 us).  Needs at least two chains of work per CTA to be worth the fix-ups.
-        if (fits_l2 && grid * 5 < (long long)sms * 4 && sc.tiles * sc.chains_per_tile >= 2LL * sms) {
+        // SM pairs; 768 x 4096 x 4096 has 96 tiles for 148 SMs): then plain stream-K over all SMs -- idle SMs cost more than the
+        // de-synchronised k positions, also beyond L2 (1792^3 68.3 -> 61.0 us, 768 x 4096 x 4096 153 -> 129 us, 1024 x 3072 x 8192
+        // 284 -> 245 us).  Needs at least two chains of work per CTA to be worth the fix-ups.
+        if (grid * 5 < (long long)sms * 4 && sc.tiles * sc.chains_per_tile >= 2LL * sms) {
             grid = sms;
             sc.k_split = 0;
         }
