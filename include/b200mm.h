@@ -189,6 +189,11 @@ B200MM_API int b200mm_mm_host(b200mm_ctx* ctx, b200mm_kernel* kern, const void* 
 /* ---- device-free introspection of the SGEMM_TC3X work schedule (no GPU needed; used by the CPU tests) --------------
  * out = {grid, full_waves, chains_per_tile, k_split, tiles, stream_k_units} for a bn x 128 tile, bk-deep stages, `sms` SMs. */
 B200MM_API int b200mm_tc3x_schedule(size_t M, size_t N, size_t K, int bn, int bk, int sms, int pure_stream_k, int out[6]);
+/* What b200mm_kernel_get(SGEMM_TC3X, M, N, K, {tune, flags}) picks on a device with `sms` SMs (tune may be NULL = all defaults):
+ * out = {tile columns 128 / 256, BK, 1 = CTA pairs (256 x 256 tiles), 1 = TMA-store epilogue, lo operands computed in shared
+ * memory (0 none, 1 B, 2 A and B), 1 = all of A split by the pre-pass, grid in CTAs, whole-tile waves, k-slices per tile (0 = none)}.
+ * N or K not a multiple of 4: the plan of the zero-padded shape. */
+B200MM_API int b200mm_tc3x_plan(size_t M, size_t N, size_t K, int sms, const uint32_t tune[4], uint32_t flags, int out[9]);
 /* Runs the kernel's own segment iterator for every CTA on the host and counts how often each (tile, chain) unit is
  * visited: cover[tile * chains_per_tile + chain] += 1 (caller zero-fills; cover_len >= tiles * chains_per_tile). */
 B200MM_API int b200mm_tc3x_schedule_cover(size_t M, size_t N, size_t K, int bn, int bk, int sms, int pure_stream_k, uint16_t* cover,

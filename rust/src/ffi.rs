@@ -132,6 +132,7 @@ extern "C" {
 
     // ---- device-free introspection of the SGEMM_TC3X work schedule ----
     pub fn b200mm_tc3x_schedule(m: usize, n: usize, k: usize, bn: c_int, bk: c_int, sms: c_int, pure_stream_k: c_int, out: *mut c_int) -> c_int;
+    pub fn b200mm_tc3x_plan(m: usize, n: usize, k: usize, sms: c_int, tune: *const u32, flags: u32, out: *mut c_int) -> c_int;
     pub fn b200mm_tc3x_schedule_cover(m: usize, n: usize, k: usize, bn: c_int, bk: c_int, sms: c_int, pure_stream_k: c_int, cover: *mut u16,
                                       cover_len: usize, max_segments_per_cta: *mut c_int, max_chains_per_cta: *mut c_int) -> c_int;
     pub fn b200mm_tc3x_schedule_replay(m: usize, n: usize, k: usize, bn: c_int, bk: c_int, sms: c_int, pure_stream_k: c_int,

@@ -289,6 +289,41 @@ def test_tc3x_schedule_reference_points():
     assert lib().b200mm_tc3x_schedule(128, 128, 128, 192, 16, 148, 0, out) != 0
 
 
+def test_tc3x_default_rules(built_lib):
+    """The shape rules of setup_tc3x, device-free (b200mm_tc3x_plan): the cases DESIGN.md 4.1 quotes, on a 148-SM device.
+    plan = (tile columns, BK, pairs, TMA store, lo operands computed in shared memory, all of A in the pre-pass, grid, whole waves, k-slices)."""
+    from wgpu_mm_b200 import lib
+
+    def plan(M, N, K, tune=None, flags=0):
+        out = (C.c_int * 9)()
+        t = (C.c_uint32 * 4)(*tune) if tune else None
+        assert lib().b200mm_tc3x_plan(M, N, K, 148, t, flags, out) == 0
+        return tuple(out)
+
+    assert plan(4096, 4096, 4096) == (256, 16, 1, 1, 0, 0, 148, 3, 0)            # pairs, 3 whole waves + stream-K tail, split pre-pass
+    assert plan(16384, 2048, 16384)[:5] == (256, 16, 1, 1, 0)                     # the 8-GPU panel
+    assert plan(1024, 1024, 1024) == (128, 32, 0, 0, 0, 0, 128, 0, 2)             # the reference's test shape: 128 x 128 tiles, 2 k-slices
+    assert plan(512, 512, 512)[:3] == (128, 32, 0)
+    assert plan(128, 4096, 4096) == (128, 32, 0, 0, 1, 1, 128, 0, 4)              # skinniest: 128 x 128 tiles + B_lo in shared memory
+    assert plan(128, 14336, 4096)[:6] == (256, 16, 0, 0, 1, 1)                    # skinny, many columns: 256-column tiles + B_lo in shared memory
+    assert plan(256, 4096, 4096)[:6] == (256, 16, 0, 0, 1, 1)                     # (the pipelined host path pins its panels to tune[3] = 2)
+    assert plan(512, 4096, 4096)[:6] == (256, 16, 0, 0, 0, 0)                     # M > 256: pre-pass
+    assert plan(2048, 2048, 2048)[:3] == (256, 16, 1) and plan(2048, 2048, 2048)[6:] == (128, 1, 1)   # L2-resident: pairs from 48 pair tiles
+    assert plan(2304, 2304, 2304)[6:] == (148, 0, 0)                              # 81 pair tiles, L2-resident: stream-K over everything
+    assert plan(3072, 3072, 3072)[6:] == (148, 1, 0)                              # beyond L2: whole waves + tail
+    assert plan(768, 4096, 4096)[2] == 1 and plan(768, 4096, 4096)[6:] == (148, 0, 0)   # 48 pair tiles would idle a third of the SMs
+    assert plan(640, 4096, 4096)[2] == 0                                          # 256-row tiles would pad 640 rows to 768
+    assert plan(1024, 4096, 4096)[2] == 1
+    assert plan(1000, 1001, 515)[:2] == plan(1000, 1004, 516)[:2]                 # ragged N / K: the padded shape's plan
+    # overrides
+    assert plan(4096, 4096, 4096, (513, 0, 0, 0))[2] == 0 and plan(1024, 1024, 1024, (512, 0, 0, 0))[2] == 1
+    assert plan(4096, 4096, 4096, (0, 0, 0, 5))[4:6] == (2, 0) and plan(4096, 4096, 4096, (0, 0, 0, 3))[4:6] == (0, 1)
+    assert plan(4096, 4096, 4096, (0, 0, 6, 0))[3] == 0 and plan(4096, 4096, 4096, (0, 0, 32, 0))[1] == 32
+    assert plan(4096, 4096, 4096, None, 1)[:5] == (256, 32, 0, 0, 0)              # B200MM_F_TC3X_1X: single-pass kernel
+    out = (C.c_int * 9)()
+    assert lib().b200mm_tc3x_plan(0, 1, 1, 148, None, 0, out) != 0
+
+
 # ---- rust/ : the reference-side crate cannot be compiled here (no cargo), so it is checked mechanically ----
 RUST = os.path.join(ROOT, "rust", "src")
 

@@ -156,6 +156,7 @@ def _declare(l: C.CDLL) -> None:
     l.b200mm_peer_barrier.argtypes = [vp, vp, C.POINTER(vp), C.c_int, C.c_int]
     l.b200mm_unshard_columns.argtypes = [vp, vp, vp, sz, sz, C.c_int]
     l.b200mm_tc3x_schedule.argtypes = [sz, sz, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    l.b200mm_tc3x_plan.argtypes = [sz, sz, sz, C.c_int, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_int)]
     l.b200mm_tc3x_schedule_cover.argtypes = [sz, sz, sz, C.c_int, C.c_int, C.c_int, C.c_int, vp, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     l.b200mm_tc3x_schedule_replay.argtypes = [sz, sz, sz, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     # wgpu_mm_c.h

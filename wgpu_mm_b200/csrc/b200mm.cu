@@ -634,6 +634,61 @@ static int setup_simt(b200mm_ctx* ctx, b200mm_kernel* k) {
     return B200MM_OK;
 }
 
+// What the default rules pick for a shape (pure: no device, no allocation) -- used by setup_tc3x and exported as b200mm_tc3x_plan so
+// that the rules are pinned by CPU tests.
+struct Tc3xPlan {
+    int bn = 256, bk = 16, split = 0;
+    bool cta2 = false, tma_store = false, a_prepass = false;
+};
+static Tc3xPlan tc3x_plan(size_t M, size_t N, size_t K, int sms, const uint32_t tune[4], bool one_pass) {
+    Tc3xPlan p;
+    p.bn = (tune[0] == 128) ? 128 : 256;
+    // Small problems (tune[0] = 0): 128 x 128 tiles when even those leave no SM without a tile (twice the tiles, so half the k-slices
+    // per tile to reach one CTA per SM and half the fix-up traffic) and B is small.  Measured (tools/small_bn.py,
+    // profiles/r2_small_bn.log): 1024^3 31.7 -> 24.3 us, 512^3 22.6 -> 16.2 us, 4096 x 512 x 512 26.9 -> 18.5 us; from 2048^3 on, and
+    // for skinny M against a big B (128 x 14336 x 4096: 90 vs 167 us), the 256-column tiles win.
+    // Against a big B the narrow tiles still pay when there are so few 256-column tiles that each would be cut into >= 8 k-slices
+    // (<= SMs / 8 tiles: skinny M with N <= 4096) -- together with B_lo computed in shared memory, see tc_split below:
+    // 128 x 4096 x 4096 54.7 -> 39.2 us, 16 x 4096 x 4096 51.3 -> 37.6 us.
+    {
+        const size_t tiles256 = ceil_div(M, 128) * ceil_div(N, 256);
+        if (tune[0] == 0 && !one_pass && tiles256 * 2 <= (size_t)sms && (K * N <= ((size_t)8 << 20) || tiles256 * 8 <= (size_t)sms)) p.bn = 128;
+    }
+    p.bk = (tune[2] == 32) ? 32 : 16;  // default: BK = 16, 4 stages
+    if (one_pass) p.bn = 256;
+    if (one_pass || p.bn == 128) p.bk = 32;  // (128 x 128 tiles with BK = 16, 6 stages: measured 8-20 % slower than BK = 32)
+    // tune[0] = 512: the 2-CTA kernel (256 x 256 tiles on CTA pairs, cta_group::2); 513: force the 1-CTA kernel.  Default: pairs when
+    // there are at least as many 256-row tiles as SM pairs (big GEMMs), single CTAs otherwise (skinny M: a pair would idle one SM).
+    {
+        const long long tiles2 = (long long)ceil_div(M, 256) * (long long)ceil_div(N, 256);
+        // (a tile count that would leave SMs idle runs as stream-K over all of them -- tc3x_make_schedule -- so pairs pay from about
+        // 2/3 of a wave on: 1792^3 63.3 -> 60.9 us, 2048^3 79.5 -> 76.1 us, 768 x 4096 x 4096 136 -> 129 us; not for a single row of
+        // pair tiles, M <= 256, where the skinny-M rules below decide)
+        const bool fits_l2 = 8.0 * ((double)M * (double)K + (double)K * (double)N) <= 100e6;
+        const long long min_tiles2 = (fits_l2 || M >= 512) ? 48 : sms / 2;
+        // 256-row tiles must not pad M much more than 128-row tiles would (640 rows: 768 vs 640 computed -- measured 126 vs 120 us)
+        const bool pad_ok = ceil_div(M, 256) * 256 == ceil_div(M, 128) * 128 || M >= 2048;
+        const bool want2 = tune[0] == 512 || (tune[0] == 0 && tiles2 >= min_tiles2 && pad_ok && getenv("B200MM_TC3X_1CTA") == nullptr);
+        p.cta2 = want2 && !one_pass && p.bn == 256 && sms % 2 == 0;
+        if (p.cta2) p.bk = (tune[2] == 32) ? 32 : 16;
+        // pair kernel: TMA-store epilogue (5 stages + double-buffered staging) unless tune[2] = 6 asks for the st.global one (6 stages)
+        p.tma_store = p.cta2 && p.bk == 16 && tune[2] != 6;
+        // lo tiles computed in shared memory (Tc3xCfg::SPLIT), available in the two default instantiations.  Measured
+        // (profiles/r2_split_shapes.log): it pays where the GEMM is bound by reading B -- skinny M: 128 x 14336 x 4096 165 -> 101 us --
+        // and costs where the tensor pipe is the bound, because the split's LDS / STS compete with the MMA's operand reads for
+        // shared-memory bandwidth (4096^3: 529 -> 554 us with B only, 607 us with A and B; 8192^3: +15 % / +64 %).
+        // tune[3]: 0 = that rule (M <= 256 and a B of >= 16 MB: B in the kernel, A -- small -- in the pre-pass; otherwise as 2),
+        // 1 = B in the kernel, A in the pre-pass, 2 = B in the pre-pass, A by row bands (pre-pass for the first wave, warp 2 for the
+        // rest), 3 = A and B in the pre-pass (round 1), 4 = B in the kernel, A by row bands, 5 = A and B in the kernel (no pre-pass)
+        const bool can_split = !one_pass && ((p.bn == 256 && p.bk == 16 && (p.tma_store || !p.cta2)) || p.bn == 128);
+        uint32_t t3 = tune[3];
+        if (t3 == 0) t3 = (can_split && M <= 256 && K * N >= ((size_t)4 << 20)) ? 1 : 2;
+        p.split = !can_split ? 0 : (t3 == 1 || t3 == 4) ? 1 : (t3 == 5 ? (p.bn == 128 ? 1 : 2) : 0);
+        p.a_prepass = (t3 == 1 || t3 == 3);
+    }
+    return p;
+}
+
 static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
     const size_t M = k->M, N = k->N, K = k->K;
     if (ctx->prop.major != 10)
@@ -661,49 +716,14 @@ static int setup_tc3x(b200mm_ctx* ctx, b200mm_kernel* k) {
         return B200MM_OK;
     }
     const bool one_pass = (k->prm.flags & B200MM_F_TC3X_1X) != 0;
-    k->tc_bn = (k->prm.tune[0] == 128) ? 128 : 256;
-    // Small problems (tune[0] = 0): 128 x 128 tiles when even those leave no SM without a tile (twice the tiles, so half the k-slices
-    // per tile to reach one CTA per SM and half the fix-up traffic) and B is small.  Measured (tools/small_bn.py,
-    // profiles/r2_small_bn.log): 1024^3 31.7 -> 24.3 us, 512^3 22.6 -> 16.2 us, 4096 x 512 x 512 26.9 -> 18.5 us; from 2048^3 on, and
-    // for skinny M against a big B (128 x 14336 x 4096: 90 vs 167 us), the 256-column tiles win.
-    // Against a big B the narrow tiles still pay when there are so few 256-column tiles that each would be cut into >= 8 k-slices
-    // (<= SMs / 8 tiles: skinny M with N <= 4096) -- together with B_lo computed in shared memory, see tc_split below:
-    // 128 x 4096 x 4096 54.7 -> 39.2 us, 16 x 4096 x 4096 51.3 -> 37.6 us.
     {
-        const size_t tiles256 = ceil_div(M, 128) * ceil_div(N, 256), sms = (size_t)ctx->prop.multiProcessorCount;
-        if (k->prm.tune[0] == 0 && !one_pass && tiles256 * 2 <= sms && (K * N <= ((size_t)8 << 20) || tiles256 * 8 <= sms)) k->tc_bn = 128;
-    }
-    k->tc_bk = (k->prm.tune[2] == 32) ? 32 : 16;  // default: BK = 16, 4 stages
-    if (one_pass) k->tc_bn = 256;
-    if (one_pass || k->tc_bn == 128) k->tc_bk = 32;  // (128 x 128 tiles with BK = 16, 6 stages: measured 8-20 % slower than BK = 32)
-    // tune[0] = 512: the 2-CTA kernel (256 x 256 tiles on CTA pairs, cta_group::2); 513: force the 1-CTA kernel.  Default: pairs when
-    // there are at least as many 256-row tiles as SM pairs (big GEMMs), single CTAs otherwise (skinny M: a pair would idle one SM).
-    {
-        const long long tiles2 = (long long)ceil_div(M, 256) * (long long)ceil_div(N, 256);
-        // (a tile count that would leave SMs idle runs as stream-K over all of them -- tc3x_make_schedule -- so pairs pay from about
-        // 2/3 of a wave on: 1792^3 63.3 -> 60.9 us, 2048^3 79.5 -> 76.1 us, 768 x 4096 x 4096 136 -> 129 us; not for a single row of
-        // pair tiles, M <= 256, where the skinny-M rules below decide)
-        const bool fits_l2 = 8.0 * ((double)M * (double)K + (double)K * (double)N) <= 100e6;
-        const long long min_tiles2 = (fits_l2 || M >= 512) ? 48 : ctx->prop.multiProcessorCount / 2;
-        // 256-row tiles must not pad M much more than 128-row tiles would (640 rows: 768 vs 640 computed -- measured 126 vs 120 us)
-        const bool pad_ok = ceil_div(M, 256) * 256 == ceil_div(M, 128) * 128 || M >= 2048;
-        const bool want2 = k->prm.tune[0] == 512 || (k->prm.tune[0] == 0 && tiles2 >= min_tiles2 && pad_ok && getenv("B200MM_TC3X_1CTA") == nullptr);
-        k->tc_cta2 = want2 && !one_pass && k->tc_bn == 256 && ctx->prop.multiProcessorCount % 2 == 0;
-        if (k->tc_cta2) k->tc_bk = (k->prm.tune[2] == 32) ? 32 : 16;
-        // pair kernel: TMA-store epilogue (5 stages + double-buffered staging) unless tune[2] = 6 asks for the st.global one (6 stages)
-        k->tc_tma_store = k->tc_cta2 && k->tc_bk == 16 && k->prm.tune[2] != 6;
-        // lo tiles computed in shared memory (Tc3xCfg::SPLIT), available in the two default instantiations.  Measured
-        // (profiles/r2_split_shapes.log): it pays where the GEMM is bound by reading B -- skinny M: 128 x 14336 x 4096 165 -> 101 us --
-        // and costs where the tensor pipe is the bound, because the split's LDS / STS compete with the MMA's operand reads for
-        // shared-memory bandwidth (4096^3: 529 -> 554 us with B only, 607 us with A and B; 8192^3: +15 % / +64 %).
-        // tune[3]: 0 = that rule (M <= 256 and a B of >= 16 MB: B in the kernel, A -- small -- in the pre-pass; otherwise as 2),
-        // 1 = B in the kernel, A in the pre-pass, 2 = B in the pre-pass, A by row bands (pre-pass for the first wave, warp 2 for the
-        // rest), 3 = A and B in the pre-pass (round 1), 4 = B in the kernel, A by row bands, 5 = A and B in the kernel (no pre-pass)
-        const bool can_split = !one_pass && ((k->tc_bn == 256 && k->tc_bk == 16 && (k->tc_tma_store || !k->tc_cta2)) || k->tc_bn == 128);
-        uint32_t t3 = k->prm.tune[3];
-        if (t3 == 0) t3 = (can_split && M <= 256 && K * N >= ((size_t)4 << 20)) ? 1 : 2;
-        k->tc_split = !can_split ? 0 : (t3 == 1 || t3 == 4) ? 1 : (t3 == 5 ? (k->tc_bn == 128 ? 1 : 2) : 0);
-        k->tc_a_prepass = (t3 == 1 || t3 == 3);
+        const Tc3xPlan p = tc3x_plan(M, N, K, ctx->prop.multiProcessorCount, k->prm.tune, one_pass);
+        k->tc_bn = p.bn;
+        k->tc_bk = p.bk;
+        k->tc_cta2 = p.cta2;
+        k->tc_tma_store = p.tma_store;
+        k->tc_split = p.split;
+        k->tc_a_prepass = p.a_prepass;
     }
     const int tile_m = k->tc_cta2 ? 256 : 128;
     // workspace: lo parts of both operands (the raw operands are consumed as hi); for N % 32 != 0 also a padded
@@ -1730,6 +1750,28 @@ extern "C" int b200mm_unshard_columns(b200mm_ctx* ctx, const void* gathered, voi
 static Tc3xSchedule tc3x_sched_for(size_t M, size_t N, size_t K, int bn, int bk, int sms, bool pure) {
     return bn == 512 ? tc3x_make_schedule(M, N, K, 256, bk, sms / 2, pure, 256) : tc3x_make_schedule(M, N, K, bn, bk, sms, pure);
 }
+extern "C" int b200mm_tc3x_plan(size_t M, size_t N, size_t K, int sms, const uint32_t tune[4], uint32_t flags, int out[9]) {
+    if (!out || !M || !N || !K || sms <= 0) return B200MM_ERR_INVALID;
+    static const uint32_t zero[4] = {0, 0, 0, 0};
+    if (!tune) tune = zero;
+    if (N % 4 || K % 4) {  // the padded path plans for the padded shape
+        N = ceil_div(N, 4) * 4;
+        K = ceil_div(K, 4) * 4;
+    }
+    const Tc3xPlan p = tc3x_plan(M, N, K, sms, tune, (flags & B200MM_F_TC3X_1X) != 0);
+    const Tc3xSchedule sc = tc3x_make_schedule(M, N, K, p.bn, p.bk, p.cta2 ? sms / 2 : sms, tune[1] == 1, p.cta2 ? 256 : 128);
+    out[0] = p.bn;
+    out[1] = p.bk;
+    out[2] = p.cta2 ? 1 : 0;
+    out[3] = p.tma_store ? 1 : 0;
+    out[4] = p.split;
+    out[5] = p.a_prepass ? 1 : 0;
+    out[6] = sc.grid * (p.cta2 ? 2 : 1);
+    out[7] = sc.full_waves;
+    out[8] = sc.k_split;
+    return B200MM_OK;
+}
+
 extern "C" int b200mm_tc3x_schedule(size_t M, size_t N, size_t K, int bn, int bk, int sms, int pure_stream_k, int out[6]) {
     if (!out || !M || !N || !K || (bn != 128 && bn != 256 && bn != 512) || (bk != 16 && bk != 32) || sms <= 0) return B200MM_ERR_INVALID;
     const Tc3xSchedule sc = tc3x_sched_for(M, N, K, bn, bk, sms, pure_stream_k != 0);
