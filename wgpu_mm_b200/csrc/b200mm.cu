@@ -83,6 +83,7 @@ struct b200mm_kernel {
     long long tc_sk_units = 0;
     // gemv
     int splits = 1, rows_per_split = 0, panels = 0, gemv_variant = 0;
+    bool gemv_blocked = false;  // grouped-scale GEMV with contiguous rows per warp (gemv.cuh BLOCKED)
     bool gemv_cluster = false;
     float* partial = nullptr;
     unsigned int* tickets = nullptr;
@@ -481,7 +482,7 @@ struct GemvPick {
 // grouped: 0 = no per-group scales, else the quantisation group size (rows).  Groups of 64 / 32 rows need a pipeline window
 // (2 x UNROLL x 16 rows) that never straddles a group: UNROLL 2 / 1 instead of 4.
 template <class T>
-static GemvPick gemv_pick(int variant, int mrows = 1, size_t grouped = 0) {
+static GemvPick gemv_pick(int variant, int mrows = 1, size_t grouped = 0, bool blocked = false) {
     if constexpr (T::COLS == 16) {
         if (grouped && grouped < 128) return grouped >= 64 ? GEMV_INST(8, 2, 16, 1, true, 2, 1) : GEMV_INST(8, 1, 16, 1, true, 2, 1);
         if (grouped) {
@@ -489,7 +490,7 @@ static GemvPick gemv_pick(int variant, int mrows = 1, size_t grouped = 0) {
                 case 11: return GEMV_INST(8, 4, 16, 1, true, 3);
                 case 12: return GEMV_INST(8, 4, 16, 1, true, 2);
                 case 14: return GEMV_INST(8, 4, 16, 1, true, 4);
-                default: return GEMV_INST(8, 4, 16, 1, true, 2, 1);
+                default: return blocked ? GEMV_INST(8, 4, 16, 1, true, 2, 1, true) : GEMV_INST(8, 4, 16, 1, true, 2, 1);
             }
         }
         if (mrows == 2) return GEMV_INST(8, 4, 16, 2);
@@ -953,11 +954,16 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     splits = (int)ceil_div(K, rps);
     k->splits = splits;
     k->rows_per_split = (int)rps;
+    // grouped scales: contiguous rows per warp (gemv.cuh BLOCKED) when every split is whole -- one fold per group and warp instead of
+    // one per pipeline window
+    k->gemv_blocked = group_k >= 128 && mrows == 1 && K % rps == 0 && rps % 128 == 0 && k->gemv_variant != 11 && k->gemv_variant != 12 &&
+                      k->gemv_variant != 14 && getenv("B200MM_GEMV_NO_BLOCKED") == nullptr;
+    const GemvFn fn_launch = k->gemv_blocked ? gemv_pick<GemvS8>(k->gemv_variant, mrows, group_k, true).fn : fn;
     k->grid = dim3(k->panels, splits, batch);
     k->block = dim3(warps * 32, 1, 1);
     k->smem = smem_for(rps);
     if (k->smem > 200 * 1024) return fail(ctx, B200MM_ERR_INVALID, "gemv: K-split too long for shared memory");
-    CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(k->smem, 48 * 1024)));
+    CU_TRY(ctx, cudaFuncSetAttribute(fn_launch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(k->smem, 48 * 1024)));
     if (splits > 1 && !k->gemv_cluster) {
         const size_t pbytes = (size_t)batch * splits * N * sizeof(float);
         const size_t tbytes = (size_t)batch * k->panels * sizeof(unsigned int);
@@ -1467,7 +1473,7 @@ extern "C" int b200mm_launch_ptr(b200mm_ctx* ctx, b200mm_kernel* k, const void* 
         case B200MM_K_GEMV_F32:
         case B200MM_K_QGEMV_SINT8: {
             const bool quant = k->id == B200MM_K_QGEMV_SINT8;
-            const GemvFn fn = (quant ? gemv_pick<GemvS8>(k->gemv_variant, (int)k->M, k->prm.group_k) : gemv_pick<GemvF32>(k->gemv_variant, (int)k->M)).fn;
+            const GemvFn fn = (quant ? gemv_pick<GemvS8>(k->gemv_variant, (int)k->M, k->prm.group_k, k->gemv_blocked) : gemv_pick<GemvF32>(k->gemv_variant, (int)k->M)).fn;
             const size_t group_k = k->prm.group_k;
             const float scale = quant ? (group_k ? 1.0f : k->prm.absmax) / 127.0f : 1.0f;
             const size_t wstride = quant ? (size_t)K * N + (group_k ? ceil_div(K, group_k) * N * 4 : 0) : (size_t)K * N * 4;

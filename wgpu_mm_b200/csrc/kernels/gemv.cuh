@@ -105,13 +105,19 @@ __device__ __forceinline__ void gemv_trace(unsigned long long* t, int idx) {
 //   partial dot product of a group is folded into the running total with ONE fma per column when the group changes, so
 //   the inner loop is the ungrouped one.  The CTA's scales (<= rows_per_split/group_k + 1 groups x PANEL columns) are
 //   staged in shared memory up front, off the critical path.
-template <class T, int WARPS, int UNROLL, int LPR, int MROWS = 1, bool GROUPED = false, int MINB = 1, int EAGER_ = -1>
+// BLOCKED (grouped scales only): warp w streams the CONTIGUOUS rows [w, w + 1) * rows_per_split / WARPS of the CTA's slab instead of
+// every WARPS-th group of RPW rows.  A thread's rows then stay inside one quantisation group for group_k / RPW loads instead of
+// 2 * UNROLL, so the per-group fold (scale * partial into the running total) runs once per group and warp -- for cfg4 with
+// group_k = 128 and 1024-row slabs exactly once, at the end -- instead of after every pipeline window.  The loop still counts in the
+// interleaved coordinate kk; prow() maps it to the physical row.  Needs whole splits (K % rows_per_split == 0, host-checked).
+template <class T, int WARPS, int UNROLL, int LPR, int MROWS = 1, bool GROUPED = false, int MINB = 1, int EAGER_ = -1, bool BLOCKED = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, float* __restrict__ y,
                    float* __restrict__ partial, unsigned int* __restrict__ tickets, int K, int N, int rows_per_split,
                    float out_scale, size_t x_batch_stride, size_t w_batch_stride_bytes, size_t y_batch_stride,
                    const __grid_constant__ PeerStore peers, int use_cluster, int group_k) {
     static_assert(!GROUPED || MROWS == 1, "grouped scales: single-row kernel only");
+    static_assert(!BLOCKED || GROUPED, "the blocked row order exists for the grouped-scale kernels");
     constexpr int COLS = T::COLS;
     constexpr int RPW = 32 / LPR;        // rows per warp per load
     constexpr int RSTEP = WARPS * RPW;   // rows per CTA per load
@@ -145,6 +151,13 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     const int k_end = min(K, k_beg + rows_per_split);
     const char* wp = Wb + (size_t)col / COLS * sizeof(typename T::Vec);
     int k = k_beg + warp * RPW + riw;
+    // physical weight row of the interleaved coordinate kk (kk - k is a multiple of RSTEP = WARPS * RPW)
+    const int k0 = k, p0 = k_beg + warp * (rows_per_split / WARPS) + riw;
+    auto prow = [&](int kk) -> int {
+        if constexpr (BLOCKED) return p0 + (int)((unsigned)(kk - k0) / (unsigned)WARPS);
+        else return kk;
+    };
+    constexpr int PSTEP = BLOCKED ? RPW : RSTEP;  // physical rows between consecutive loads of a thread
 
     // Software pipeline: the loads of batch i+1 are issued before batch i is consumed, and the very first batch is
     // issued BEFORE x is staged, so its DRAM latency overlaps the staging barrier (every serialized ~1 us matters in
@@ -163,9 +176,10 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     typename T::Vec wa[UNROLL], wb[UNROLL];
     auto issue = [&](typename T::Vec (&w)[UNROLL], int kk) {
+        const int pk = prow(kk);
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
-            if (col_ok && kk + u * RSTEP < k_end) w[u] = T::load(wp + (size_t)(kk + u * RSTEP) * row_pitch);
+            if (col_ok && kk + u * RSTEP < k_end) w[u] = T::load(wp + (size_t)(pk + u * PSTEP) * row_pitch);
     };
     // fp32: both register buffers are in flight before anything dependent is touched (58.7 MB shape: 12.8 -> 10.7 us).
     // sint8 keeps one (the longer live ranges cost it an occupancy step: measured 15.6 -> 19 us with both).
@@ -223,7 +237,7 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     if constexpr (GROUPED) {
 #pragma unroll
         for (int j = 0; j < COLS / 4; ++j) tot4[j * (WARPS * 32) + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
-        cur_g = k / group_k;
+        cur_g = prow(k) / group_k;
     }
     auto fold = [&](int g) {
         if constexpr (GROUPED) {
@@ -255,30 +269,33 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     };
 
     auto consume = [&](const typename T::Vec (&w)[UNROLL], int kk) {
+        const int pk = prow(kk);
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
             if (col_ok && kk + u * RSTEP < k_end) {
 #pragma unroll
-                for (int m = 0; m < MROWS; ++m) T::fma(acc[m], w[u], xs[m * rows_per_split + kk + u * RSTEP - k_beg]);
+                for (int m = 0; m < MROWS; ++m) T::fma(acc[m], w[u], xs[m * rows_per_split + pk + u * PSTEP - k_beg]);
             }
     };
     // Fast path: while a whole double batch (and the loads it issues ahead) is in range, no per-vector bounds
     // bookkeeping -- in the sint8 kernel that bookkeeping was ~14 of 52 instructions per 16 weights.
     auto issue_fast = [&](typename T::Vec (&w)[UNROLL], int kk) {
+        const int pk = prow(kk);
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) w[u] = T::load(wp + (size_t)(kk + u * RSTEP) * row_pitch);
+        for (int u = 0; u < UNROLL; ++u) w[u] = T::load(wp + (size_t)(pk + u * PSTEP) * row_pitch);
     };
     auto consume_fast = [&](const typename T::Vec (&w)[UNROLL], int kk) {
+        const int pk = prow(kk);
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
-            for (int m = 0; m < MROWS; ++m) T::fma(acc[m], w[u], xs[m * rows_per_split + kk + u * RSTEP - k_beg]);
+            for (int m = 0; m < MROWS; ++m) T::fma(acc[m], w[u], xs[m * rows_per_split + pk + u * PSTEP - k_beg]);
         }
     };
     if (col_ok) {
         constexpr int AHEAD = (EAGER ? 4 : 3) * UNROLL - 1;  // furthest row-step touched by one fast iteration
         for (; k + AHEAD * RSTEP < k_end; k += 2 * UNROLL * RSTEP) {
-            group_step(k);
+            group_step(prow(k));
             if constexpr (EAGER) {
                 consume_fast(wa, k);
                 issue_fast(wa, k + 2 * UNROLL * RSTEP);
@@ -294,7 +311,7 @@ gemv_stream_kernel(const float* __restrict__ x, const void* __restrict__ W, floa
     }
     // guarded remainder (same buffer invariants: wa holds rows k.., and for EAGER wb holds rows k + UNROLL*RSTEP..)
     for (; k < k_end; k += 2 * UNROLL * RSTEP) {
-        group_step(k);
+        group_step(prow(k));
         if constexpr (EAGER) {
             consume(wa, k);
             issue(wa, k + 2 * UNROLL * RSTEP);
