@@ -484,7 +484,8 @@ struct GemvPick {
 template <class T>
 static GemvPick gemv_pick(int variant, int mrows = 1, size_t grouped = 0, bool blocked = false) {
     if constexpr (T::COLS == 16) {
-        if (grouped && grouped < 128) return grouped >= 64 ? GEMV_INST(8, 2, 16, 1, true, 2, 1) : GEMV_INST(8, 1, 16, 1, true, 2, 1);
+        // (with the blocked row order a thread's 16-row window never straddles a multiple of 32, so the UNROLL 4 kernel serves these too)
+        if (grouped && grouped < 128 && !blocked) return grouped >= 64 ? GEMV_INST(8, 2, 16, 1, true, 2, 1) : GEMV_INST(8, 1, 16, 1, true, 2, 1);
         if (grouped) {
             switch (variant) {
                 case 11: return GEMV_INST(8, 4, 16, 1, true, 3);
@@ -870,7 +871,9 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
         if (group_k != 32 && group_k != 64 && group_k % 128)
             return fail(ctx, B200MM_ERR_INVALID, "qgemv_sint8: group_k must be 32, 64 or a multiple of 128 (got %zu)", group_k);
     }
-    const GemvPick pick = quant ? gemv_pick<GemvS8>(k->gemv_variant, mrows, group_k) : gemv_pick<GemvF32>(k->gemv_variant, mrows);
+    // groups of 32 / 64 rows: plan the geometry with the blocked UNROLL 4 kernel (it is the one that runs when every split is whole)
+    const bool try_blocked = group_k && group_k < 128 && mrows == 1 && getenv("B200MM_GEMV_NO_BLOCKED") == nullptr;
+    const GemvPick pick = quant ? gemv_pick<GemvS8>(k->gemv_variant, mrows, group_k, try_blocked) : gemv_pick<GemvF32>(k->gemv_variant, mrows);
     const GemvFn fn = pick.fn;
     const int warps = pick.warps, lpr = pick.lpr;
     const int panel = lpr * cols;
@@ -897,7 +900,7 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
         const size_t slots = (size_t)ctx->prop.multiProcessorCount * occ;
         splits = (int)(slots / ((size_t)k->panels * batch));
         splits = std::max(1, std::min(splits, 64));
-        if (quant && !group_k && mrows == 1) {
+        if (quant && mrows == 1) {  // (grouped scales too: equal, whole splits are also what the blocked row order needs -- cfg4 group_k = 128: 5 splits 19.1 us, 4 splits 13.55 us)
             // sint8 at 2 CTAs/SM: a power-of-two count keeps the K-splits equal (no guarded remainder) and leaves CTA slots free
             // for the next programmatic-dependent launch to become resident and prefetch (cfg4: 4 splits 12.75 us, 5 splits 18.2 us)
             int p2 = 1;
@@ -915,7 +918,8 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
         else
             splits = 8;
     }
-    const int rstep = group_k ? (int)std::min<size_t>(group_k, 128) : warps * (32 / lpr);  // grouped: splits start on a pipeline-window boundary
+    // grouped: splits start on a pipeline-window boundary (blocked row order: on a 128-row boundary, so that every warp's block is whole)
+    const int rstep = group_k ? (try_blocked ? 128 : (int)std::min<size_t>(group_k, 128)) : warps * (32 / lpr);
     auto smem_for = [&](size_t rows) {
         size_t b = ((size_t)mrows * rows + (size_t)warps * mrows * panel + (size_t)8 * mrows * panel) * sizeof(float);  // x, warp partials, 8 cluster receive slots
         if (group_k) b += ((rows / group_k + 2) * panel + (size_t)warps * 32 * cols) * sizeof(float);  // scales + per-thread totals
@@ -956,9 +960,9 @@ static int setup_gemv(b200mm_ctx* ctx, b200mm_kernel* k, bool quant) {
     k->rows_per_split = (int)rps;
     // grouped scales: contiguous rows per warp (gemv.cuh BLOCKED) when every split is whole -- one fold per group and warp instead of
     // one per pipeline window
-    k->gemv_blocked = group_k >= 128 && mrows == 1 && K % rps == 0 && rps % 128 == 0 && k->gemv_variant != 11 && k->gemv_variant != 12 &&
+    k->gemv_blocked = group_k >= 32 && mrows == 1 && K % rps == 0 && rps % 128 == 0 && k->gemv_variant != 11 && k->gemv_variant != 12 &&
                       k->gemv_variant != 14 && getenv("B200MM_GEMV_NO_BLOCKED") == nullptr;
-    const GemvFn fn_launch = k->gemv_blocked ? gemv_pick<GemvS8>(k->gemv_variant, mrows, group_k, true).fn : fn;
+    const GemvFn fn_launch = quant ? gemv_pick<GemvS8>(k->gemv_variant, mrows, group_k, k->gemv_blocked).fn : fn;
     k->grid = dim3(k->panels, splits, batch);
     k->block = dim3(warps * 32, 1, 1);
     k->smem = smem_for(rps);
