@@ -324,6 +324,41 @@ def test_tc3x_default_rules(built_lib):
     assert lib().b200mm_tc3x_plan(0, 1, 1, 148, None, 0, out) != 0
 
 
+@pytest.mark.parametrize("rows_per_split", [128, 256, 1024, 2048, 4096])
+@pytest.mark.parametrize("group_k", [32, 64, 128, 256, 512])
+def test_gemv_blocked_row_order_model(rows_per_split, group_k):
+    """Arithmetic model of gemv.cuh's BLOCKED row order (the index math restated, WARPS = 8, LPR = 16 -> RPW = 2, UNROLL = 4): the
+    loop counts in the interleaved coordinate kk and prow() maps it to the physical row.  Every row of the slab is visited
+    exactly once, a thread's rows ascend, one loop iteration (2 * UNROLL loads) never straddles a quantisation group, and at
+    most one group boundary is crossed between consecutive iterations -- the three facts the per-group fold relies on."""
+    WARPS, RPW, UNROLL = 8, 2, 4
+    RSTEP = WARPS * RPW
+    k_beg = 3 * rows_per_split  # some split in the middle of K
+    k_end = k_beg + rows_per_split
+    seen = np.zeros(rows_per_split, dtype=np.int32)
+    for warp in range(WARPS):
+        for riw in range(RPW):
+            k0 = k_beg + warp * RPW + riw
+            p0 = k_beg + warp * (rows_per_split // WARPS) + riw
+            prow = lambda kk: p0 + (kk - k0) // WARPS
+            last_group, last_row = None, -1
+            k = k0
+            while k < k_end:
+                rows = [prow(k) + u * RPW for u in range(2 * UNROLL) if k + u * RSTEP < k_end]
+                groups = {r // group_k for r in rows}
+                assert len(groups) == 1, "an iteration straddles a group"
+                g = groups.pop()
+                assert g == prow(k) // group_k  # group_step() looks at the iteration's first row only
+                assert last_group is None or g - last_group in (0, 1)
+                assert rows[0] > last_row and rows == sorted(rows)
+                last_group, last_row = g, rows[-1]
+                for r in rows:
+                    assert k_beg <= r < k_end
+                    seen[r - k_beg] += 1
+                k += 2 * UNROLL * RSTEP
+    assert (seen == 1).all()
+
+
 # ---- rust/ : the reference-side crate cannot be compiled here (no cargo), so it is checked mechanically ----
 RUST = os.path.join(ROOT, "rust", "src")
 
